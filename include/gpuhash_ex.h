@@ -1,0 +1,160 @@
+/*
+ * gpuhash_ex.h -- extended C ABI of the B200-native Mega-KV hash index.
+ *
+ * Plain C: pointers, sizes and integers only (streams travel as void*), so it can
+ * be bound from C, cgo, ctypes ... without CUDA headers.  The three legacy entry
+ * points of libgpuhash.h are thin wrappers over the *_ex calls below using the
+ * process-wide default geometry.
+ *
+ * What each group replaces in the reference (pzrq/megakv):
+ *   geometry            compile-time macros of libgpuhash/gpu_hash.h:46-76
+ *   *_ex launches       gpu_hash_search / _insert / _delete, gpu_hash.cu:482-593
+ *   gpuhash_index_*     the per-cycle transfer + launch loop of the scheduler,
+ *                       src/mega_scheduler.c:392-504, and the pinned/device batch
+ *                       buffers of src/mega_recv.c:120-213
+ *   gpuhash_bench_*     the micro-benchmarks libgpuhash/test/back/ *_stream.c
+ *   gpuhash_dev_* etc.  cudaMalloc/cudaMemcpy plumbing the reference's tests do inline
+ *
+ * All functions return 0 on success or a cudaError_t value (> 0); -1 = bad argument.
+ */
+#ifndef GPUHASH_EX_H
+#define GPUHASH_EX_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUHASH_CUCKOO   0u     /* HASH_CUCKOO   gpu_hash.h:73 */
+#define GPUHASH_2CHOICE  1u     /* HASH_2CHOICE  gpu_hash.h:72 */
+
+/* insert flags */
+#define GPUHASH_INSERT_SERIAL  1u   /* one thread, batch order: slot-for-slot equal to a sequential run */
+
+typedef struct gpuhash_geom_s {
+	uint32_t hash_mask;     /* buckets of this table - 1 (a shard holds a slice of the logical table) */
+	uint32_t block_mask;    /* BLOCK_HASH_MASK of the LOGICAL table: low bits the alternate bucket may change */
+	uint32_t algo;          /* GPUHASH_CUCKOO | GPUHASH_2CHOICE */
+	uint32_t max_cuckoo;    /* MAX_CUCKOO_NUM (5) */
+} gpuhash_geom_t;
+
+typedef struct gpuhash_stats_s {
+	unsigned long long ins_skipped, ins_updated, ins_placed_b1, ins_placed_b2, ins_to_b2,
+	                   ins_displaced, ins_dropped, ins_overwritten, ins_cas_retry, ins_gave_up,
+	                   chain_hist[8],
+	                   del_zeroed, del_requests_hit,
+	                   search_hits_b1, search_hits_b2;
+} gpuhash_stats_t;
+
+/* ---- geometry ---- */
+int    gpuhash_geom_init(gpuhash_geom_t *g, int mem_p, unsigned algo);
+/* shard `log2_shards` of a logical 2^mem_p_total-byte table: local table is 2^(mem_p_total-log2_shards) bytes */
+int    gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int log2_shards, unsigned algo);
+size_t gpuhash_table_bytes(const gpuhash_geom_t *g);
+void   gpuhash_set_default_geom(const gpuhash_geom_t *g);   /* what the 3 legacy entry points use */
+void   gpuhash_get_default_geom(gpuhash_geom_t *g);
+
+/* ---- launch tuning (process-wide; defaults are what bench.py measures) ---- */
+typedef struct gpuhash_tune_s {
+	int search_qpt;          /* requests per thread: 1, 2 or 4; 0 = choose from batch size */
+	int search_prefetch_loc; /* 1: L2::64B hint on signature-row loads (pulls the location sector) */
+	int insert_ctas_per_sm;  /* grid of the count-independent insert kernel */
+} gpuhash_tune_t;
+void   gpuhash_set_tuning(const gpuhash_tune_t *t);
+void   gpuhash_get_tuning(gpuhash_tune_t *t);
+
+/* ---- asynchronous launches on device pointers (stream: cudaStream_t as void*, NULL = default) ---- */
+int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, void *out_d, const void *table_d,
+		size_t n, gpuhash_stats_t *stats_d, void *stream);
+int gpuhash_insert_ex(const gpuhash_geom_t *g, void *table_d, const void *const *blk_input_d,
+		const int *blk_elem_num_d, int num_blks, gpuhash_stats_t *stats_d, unsigned flags, void *stream);
+int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *ielem_d, size_t n,
+		gpuhash_stats_t *stats_d, unsigned flags, void *stream);
+int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_d, size_t n,
+		gpuhash_stats_t *stats_d, unsigned flags, void *stream);
+
+/* ---- device / pinned memory and stream plumbing ---- */
+int   gpuhash_device_count(void);
+int   gpuhash_set_device(int dev);
+int   gpuhash_device_info(int dev, int *sm_count, int *l2_bytes, size_t *free_bytes, size_t *total_bytes);
+void *gpuhash_dev_alloc(size_t bytes);                 /* NULL on failure */
+int   gpuhash_dev_free(void *p);
+int   gpuhash_dev_memset(void *p, int v, size_t bytes, void *stream);
+int   gpuhash_h2d(void *dst_d, const void *src_h, size_t bytes, void *stream);   /* async when src is pinned */
+int   gpuhash_d2h(void *dst_h, const void *src_d, size_t bytes, void *stream);
+void *gpuhash_host_alloc(size_t bytes);                /* pinned */
+int   gpuhash_host_free(void *p);
+void *gpuhash_stream_create(void);
+int   gpuhash_stream_destroy(void *stream);
+int   gpuhash_stream_sync(void *stream);
+int   gpuhash_device_sync(void);
+void *gpuhash_event_create(void);
+int   gpuhash_event_destroy(void *ev);
+int   gpuhash_event_record(void *ev, void *stream);
+int   gpuhash_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
+const char *gpuhash_error_string(int err);
+const char *gpuhash_build_info(void);
+
+/* ---- roofline probe: n random 32 B sectors read from `table_d` (bytes must be a power of two) ----
+ * mode 0: signature sector of a random 64 B bucket; 1: any random 32 B sector; 2: whole random 64 B bucket.
+ * Writes the kernel time of the best of `iters` launches. */
+int gpuhash_roofline_gather(const void *table_d, size_t table_bytes, size_t n, int mode,
+		int loads_per_thread, int iters, float *best_ms, void *stream);
+
+/* ---- the scheduler's device side: an index that owns its table, streams and staging ---- */
+typedef struct gpuhash_index_s gpuhash_index_t;
+
+/* workers = number of independent batch slots (reference: one per CPU receiver, <= 16, each with its
+ * own stream, mega_scheduler.c:276-280); capacities are per worker per cycle (mega.c:136,143-144). */
+gpuhash_index_t *gpuhash_index_create(int mem_p, unsigned algo, int workers,
+		size_t max_search, size_t max_insert, size_t max_delete);
+void   gpuhash_index_destroy(gpuhash_index_t *ix);
+void  *gpuhash_index_table(gpuhash_index_t *ix);                       /* device pointer */
+const gpuhash_geom_t *gpuhash_index_geom(const gpuhash_index_t *ix);
+void  *gpuhash_index_stream(gpuhash_index_t *ix, int worker);
+int    gpuhash_index_clear(gpuhash_index_t *ix);
+int    gpuhash_index_load(gpuhash_index_t *ix, const void *table_h);   /* reference byte layout */
+int    gpuhash_index_dump(gpuhash_index_t *ix, void *table_h);
+int    gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset);
+int    gpuhash_index_enable_stats(gpuhash_index_t *ix, int on);
+
+/* One scheduler cycle for one worker with HOST buffers (pinned or pageable), in the reference's order
+ * search -> delete -> insert on the worker's stream (mega_scheduler.c:392-502).  Asynchronous: results
+ * are in search_out_h after gpuhash_index_sync().  Any of the three parts may be empty. */
+int gpuhash_index_submit(gpuhash_index_t *ix, int worker,
+		const void *search_in_h, size_t n_search, void *search_out_h,
+		const void *delete_in_h, size_t n_delete,
+		const void *insert_in_h, size_t n_insert);
+int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_scheduler.c:504 */
+
+/* ---- timed loops (CUDA events on the launching streams; the Python bench only orchestrates) ---- */
+typedef struct gpuhash_bench_result_s {
+	float  total_ms;        /* first launch -> last completion, events */
+	float  search_ms;       /* summed per-launch device time of the search kernels (serial leg only) */
+	unsigned long long launches;
+	unsigned long long search_ops, insert_ops, delete_ops;
+	unsigned long long h2d_bytes, d2h_bytes;
+} gpuhash_bench_result_t;
+
+/* Device-resident mixed workload: `steps` batches laid out back to back in device memory
+ * (search_d: steps*n_search selem_t, insert_d: steps*n_insert ielem_t, out_d: steps*2*n_search loc_t),
+ * issued round-robin over `streams` streams, one search launch + one insert launch per batch.
+ * use_graph != 0: the whole issue sequence is captured once into a CUDA graph and the graph launch is
+ * what gets timed (removes the host's per-launch cost, not the device's). */
+int gpuhash_bench_resident(const gpuhash_geom_t *g, void *table_d,
+		const void *search_d, size_t n_search, void *out_d,
+		const void *insert_d, size_t n_insert,
+		int steps, int streams, int use_graph, gpuhash_bench_result_t *res);
+
+/* Same workload through gpuhash_index_submit with pinned host buffers (H2D + D2H inside the timing). */
+int gpuhash_bench_e2e(gpuhash_index_t *ix,
+		const void *search_h, size_t n_search, void *out_h,
+		const void *insert_h, size_t n_insert,
+		int steps, gpuhash_bench_result_t *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

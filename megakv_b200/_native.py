@@ -1,0 +1,135 @@
+"""ctypes view of megakv_b200/lib/libgpuhash.so (the C ABI declared in include/*.h).
+
+There is no fallback: if the shared library is missing, or a call is made without a CUDA
+device, this module raises.  Nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgpuhash.so")
+
+CUCKOO, TWO_CHOICE = 0, 1
+INSERT_SERIAL = 1
+
+
+class Geom(C.Structure):                      # gpuhash_geom_t
+    _fields_ = [("hash_mask", C.c_uint32), ("block_mask", C.c_uint32),
+                ("algo", C.c_uint32), ("max_cuckoo", C.c_uint32)]
+
+
+class Stats(C.Structure):                     # gpuhash_stats_t
+    _names = ("ins_skipped", "ins_updated", "ins_placed_b1", "ins_placed_b2", "ins_to_b2",
+              "ins_displaced", "ins_dropped", "ins_overwritten", "ins_cas_retry", "ins_gave_up")
+    _tail = ("del_zeroed", "del_requests_hit", "search_hits_b1", "search_hits_b2")
+    _fields_ = ([(n, C.c_ulonglong) for n in _names] + [("chain_hist", C.c_ulonglong * 8)]
+                + [(n, C.c_ulonglong) for n in _tail])
+
+    def as_dict(self):
+        d = {n: int(getattr(self, n)) for n in self._names + self._tail}
+        d["chain_hist"] = [int(v) for v in self.chain_hist]
+        return d
+
+
+class Tune(C.Structure):                      # gpuhash_tune_t
+    _fields_ = [("search_qpt", C.c_int), ("search_prefetch_loc", C.c_int), ("insert_ctas_per_sm", C.c_int)]
+
+
+class BenchResult(C.Structure):               # gpuhash_bench_result_t
+    _fields_ = [("total_ms", C.c_float), ("search_ms", C.c_float), ("launches", C.c_ulonglong),
+                ("search_ops", C.c_ulonglong), ("insert_ops", C.c_ulonglong), ("delete_ops", C.c_ulonglong),
+                ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong)]
+
+
+# every symbol include/*.h declares: name -> (restype, argtypes)
+_vp, _sz, _i, _u = C.c_void_p, C.c_size_t, C.c_int, C.c_uint
+_gp, _sp = C.POINTER(Geom), C.POINTER(Stats)
+SYMBOLS = {
+    # libgpuhash.h (legacy ABI, reference libgpuhash.h:29-62)
+    "gpu_hash_search": (None, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gpu_hash_insert": (None, [_vp, _vp, _vp, _i, _vp]),
+    "gpu_hash_delete": (None, [_vp, _vp, _i, _i, _i, _vp]),
+    "gpu_delete_insert": (None, [_vp, _vp, C.c_uint32, _vp, _vp, _i, C.c_uint32, C.c_uint32, _vp]),
+    # gpuhash_ex.h
+    "gpuhash_geom_init": (_i, [_gp, _i, _u]),
+    "gpuhash_geom_init_shard": (_i, [_gp, _i, _i, _u]),
+    "gpuhash_table_bytes": (_sz, [_gp]),
+    "gpuhash_set_default_geom": (None, [_gp]),
+    "gpuhash_get_default_geom": (None, [_gp]),
+    "gpuhash_set_tuning": (None, [C.POINTER(Tune)]),
+    "gpuhash_get_tuning": (None, [C.POINTER(Tune)]),
+    "gpuhash_search_ex": (_i, [_gp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_insert_ex": (_i, [_gp, _vp, _vp, _vp, _i, _vp, _u, _vp]),
+    "gpuhash_insert_flat_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "gpuhash_delete_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "gpuhash_device_count": (_i, []),
+    "gpuhash_set_device": (_i, [_i]),
+    "gpuhash_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
+    "gpuhash_dev_alloc": (_vp, [_sz]),
+    "gpuhash_dev_free": (_i, [_vp]),
+    "gpuhash_dev_memset": (_i, [_vp, _i, _sz, _vp]),
+    "gpuhash_h2d": (_i, [_vp, _vp, _sz, _vp]),
+    "gpuhash_d2h": (_i, [_vp, _vp, _sz, _vp]),
+    "gpuhash_host_alloc": (_vp, [_sz]),
+    "gpuhash_host_free": (_i, [_vp]),
+    "gpuhash_stream_create": (_vp, []),
+    "gpuhash_stream_destroy": (_i, [_vp]),
+    "gpuhash_stream_sync": (_i, [_vp]),
+    "gpuhash_device_sync": (_i, []),
+    "gpuhash_event_create": (_vp, []),
+    "gpuhash_event_destroy": (_i, [_vp]),
+    "gpuhash_event_record": (_i, [_vp, _vp]),
+    "gpuhash_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
+    "gpuhash_error_string": (C.c_char_p, [_i]),
+    "gpuhash_build_info": (C.c_char_p, []),
+    "gpuhash_roofline_gather": (_i, [_vp, _sz, _sz, _i, _i, _i, C.POINTER(C.c_float), _vp]),
+    "gpuhash_index_create": (_vp, [_i, _u, _i, _sz, _sz, _sz]),
+    "gpuhash_index_destroy": (None, [_vp]),
+    "gpuhash_index_table": (_vp, [_vp]),
+    "gpuhash_index_geom": (_gp, [_vp]),
+    "gpuhash_index_stream": (_vp, [_vp, _i]),
+    "gpuhash_index_clear": (_i, [_vp]),
+    "gpuhash_index_load": (_i, [_vp, _vp]),
+    "gpuhash_index_dump": (_i, [_vp, _vp]),
+    "gpuhash_index_stats": (_i, [_vp, _sp, _i]),
+    "gpuhash_index_enable_stats": (_i, [_vp, _i]),
+    "gpuhash_index_submit": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
+    "gpuhash_index_sync": (_i, [_vp]),
+    "gpuhash_bench_resident": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),
+    "gpuhash_bench_e2e": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, C.POINTER(BenchResult)]),
+}
+
+_lib = None
+
+
+class GpuHashError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library with every prototype applied.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpuHashError(
+                f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()). "
+                "megakv_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)            # AttributeError if a declared symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().gpuhash_error_string(rc).decode()
+        raise GpuHashError(f"{what or 'libgpuhash'} failed: {rc} ({msg})")
+
+
+def require_gpu():
+    n = lib().gpuhash_device_count()
+    if n < 1:
+        raise GpuHashError("no CUDA device visible; megakv_b200 has no CPU fallback")
+    return n

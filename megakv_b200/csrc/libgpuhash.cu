@@ -1,0 +1,367 @@
+/*
+ * libgpuhash.cu -- host side of the launches: the legacy C ABI (libgpuhash.h), the
+ * run-time-geometry *_ex calls (gpuhash_ex.h), the device/stream plumbing and the
+ * random-sector roofline probe.
+ *
+ * Built without exceptions/RTTI and without any libstdc++ symbol, so the static
+ * archive links with plain `gcc ... -lgpuhash -lcudart` exactly like the reference's
+ * (src/Makefile:26; src/mega.c:23-27 fakes __gxx_personality_v0 for the same reason).
+ *
+ * There is no CPU fallback anywhere in this file: every operation is a kernel launch.
+ */
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "libgpuhash.h"
+#include "gpuhash_ex.h"
+#include "gpuhash_kernels.cuh"
+
+static_assert(sizeof(bucket_t) == 64 && sizeof(gh::Bucket) == 64, "bucket_t must be 64 B (gpu_hash.h:79-82)");
+static_assert(sizeof(selem_t) == 8 && sizeof(ielem_t) == 12, "request layouts (gpu_hash.h:85-104)");
+static_assert(sizeof(gpuhash_geom_t) == sizeof(gh::Geom), "geom mirror");
+static_assert(sizeof(gpuhash_stats_t) == sizeof(gh::Stats), "stats mirror");
+
+#if defined(HASH_2CHOICE)
+#  define GH_DEFAULT_ALGO GPUHASH_2CHOICE
+#else
+#  define GH_DEFAULT_ALGO GPUHASH_CUCKOO
+#endif
+
+/* process-wide defaults of the legacy entry points = the header this file was compiled with */
+static gpuhash_geom_t g_default_geom = {
+	(uint32_t)HASH_MASK, (uint32_t)BLOCK_HASH_MASK, GH_DEFAULT_ALGO, 5u
+};
+static gpuhash_tune_t g_tune = { 0, 0, 4 };
+
+static int g_sm_count[64];          /* 0 = not queried yet */
+
+static int sm_count_now(void)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+	if (g_sm_count[dev] == 0) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+		g_sm_count[dev] = n;
+	}
+	return g_sm_count[dev];
+}
+
+static inline gh::Geom to_geom(const gpuhash_geom_t *g)
+{
+	gh::Geom r; r.hash_mask = g->hash_mask; r.block_mask = g->block_mask; r.algo = g->algo; r.max_cuckoo = g->max_cuckoo;
+	return r;
+}
+
+/* ------------------------------------------------------------------ geometry */
+
+extern "C" int gpuhash_geom_init(gpuhash_geom_t *g, int mem_p, unsigned algo)
+{
+	return gpuhash_geom_init_shard(g, mem_p, 0, algo);
+}
+
+extern "C" int gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int log2_shards, unsigned algo)
+{
+	/* BUC_P = 6, IBLOCK_P = 3 (gpu_hash.h:57,67).  hash_t is 32 bits => at most 2^32 buckets, MEM_P <= 38;
+	 * the alternate bucket keeps the top 3 bits of the bucket index, so at most 8 shards stay closed. */
+	if (!g || algo > GPUHASH_2CHOICE || log2_shards < 0 || log2_shards > 3) return -1;
+	if (mem_p_total < 6 + 3 || mem_p_total > 38) return -1;
+	g->hash_mask  = (uint32_t)((1ULL << (mem_p_total - 6 - log2_shards)) - 1);
+	g->block_mask = (uint32_t)((1ULL << (mem_p_total - 6 - 3)) - 1);
+	g->algo = algo;
+	g->max_cuckoo = 5;
+	return 0;
+}
+
+extern "C" size_t gpuhash_table_bytes(const gpuhash_geom_t *g)
+{
+	return ((size_t)g->hash_mask + 1) * sizeof(gh::Bucket);
+}
+
+extern "C" void gpuhash_set_default_geom(const gpuhash_geom_t *g) { g_default_geom = *g; }
+extern "C" void gpuhash_get_default_geom(gpuhash_geom_t *g) { *g = g_default_geom; }
+extern "C" void gpuhash_set_tuning(const gpuhash_tune_t *t) { g_tune = *t; }
+extern "C" void gpuhash_get_tuning(gpuhash_tune_t *t) { *t = g_tune; }
+
+/* ------------------------------------------------------------------ launches */
+
+template <int kQpt>
+static void launch_search(const uint2 *in, uint2 *out, const gh::Bucket *table, size_t n,
+		const gh::Geom &g, gh::Stats *st, cudaStream_t s)
+{
+	size_t blocks = (n + (size_t)256 * kQpt - 1) / ((size_t)256 * kQpt);
+	if (blocks > 0x7fffffffULL) blocks = 0x7fffffffULL;
+	if (g_tune.search_prefetch_loc)
+		gh::search_kernel<kQpt, true><<<(unsigned)blocks, 256, 0, s>>>(in, out, table, n, g, st);
+	else
+		gh::search_kernel<kQpt, false><<<(unsigned)blocks, 256, 0, s>>>(in, out, table, n, g, st);
+}
+
+extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, void *out_d,
+		const void *table_d, size_t n, gpuhash_stats_t *stats_d, void *stream)
+{
+	if (!g || (n && (!selem_d || !out_d || !table_d))) return -1;
+	if (n == 0) return 0;
+	int qpt = g_tune.search_qpt;
+	if (qpt == 0) {
+		/* one request per thread until every SM has a full complement of warps, then add
+		 * independent loads per thread instead of more (queued) CTAs */
+		size_t full = (size_t)sm_count_now() * 2048;
+		qpt = n <= full ? 1 : (n <= 4 * full ? 2 : 4);
+	}
+	const uint2 *in = (const uint2 *)selem_d; uint2 *out = (uint2 *)out_d;
+	const gh::Bucket *t = (const gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
+	cudaStream_t s = (cudaStream_t)stream;
+	gh::Geom gg = to_geom(g);
+	if (qpt >= 4)      launch_search<4>(in, out, t, n, gg, st, s);
+	else if (qpt >= 2) launch_search<2>(in, out, t, n, gg, st, s);
+	else               launch_search<1>(in, out, t, n, gg, st, s);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_insert_ex(const gpuhash_geom_t *g, void *table_d, const void *const *blk_input_d,
+		const int *blk_elem_num_d, int num_blks, gpuhash_stats_t *stats_d, unsigned flags, void *stream)
+{
+	if (!g || num_blks < 0 || (num_blks && (!table_d || !blk_input_d || !blk_elem_num_d))) return -1;
+	if (num_blks == 0) return 0;
+	cudaStream_t s = (cudaStream_t)stream;
+	gh::Geom gg = to_geom(g);
+	if (flags & GPUHASH_INSERT_SERIAL) {
+		gh::insert_serial_kernel<<<1, 32, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *const *)blk_input_d,
+				blk_elem_num_d, num_blks, nullptr, 0, gg, (gh::Stats *)stats_d);
+	} else {
+		int per_sm = g_tune.insert_ctas_per_sm > 0 ? g_tune.insert_ctas_per_sm : 4;
+		unsigned blocks = (unsigned)(sm_count_now() * per_sm);
+		gh::insert_segments_kernel<<<blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+				(const uint32_t *const *)blk_input_d, blk_elem_num_d, num_blks, gg, (gh::Stats *)stats_d);
+	}
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *ielem_d, size_t n,
+		gpuhash_stats_t *stats_d, unsigned flags, void *stream)
+{
+	if (!g || (n && (!table_d || !ielem_d))) return -1;
+	if (n == 0) return 0;
+	cudaStream_t s = (cudaStream_t)stream;
+	gh::Geom gg = to_geom(g);
+	if (flags & GPUHASH_INSERT_SERIAL) {
+		gh::insert_serial_kernel<<<1, 32, 0, s>>>((gh::Bucket *)table_d, nullptr, nullptr, 0,
+				(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+	} else {
+		size_t blocks = (n + 255) / 256;
+		size_t cap = (size_t)sm_count_now() * 32;        /* grid-stride beyond 32 CTAs per SM */
+		if (blocks > cap) blocks = cap;
+		gh::insert_flat_kernel<<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+				(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+	}
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_d, size_t n,
+		gpuhash_stats_t *stats_d, unsigned flags, void *stream)
+{
+	if (!g || (n && (!table_d || !delem_d))) return -1;
+	if (n == 0) return 0;
+	cudaStream_t s = (cudaStream_t)stream;
+	gh::Geom gg = to_geom(g);
+	if (flags & GPUHASH_INSERT_SERIAL) {
+		gh::delete_serial_kernel<<<1, 32, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg,
+				(gh::Stats *)stats_d);
+	} else {
+		size_t blocks = (n + 255) / 256;
+		size_t cap = (size_t)sm_count_now() * 32;
+		if (blocks > cap) blocks = cap;
+		gh::delete_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg,
+				(gh::Stats *)stats_d);
+	}
+	return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ legacy C ABI */
+
+/* reference gpu_hash.cu:482-518.  num_thread / threads_per_blk described the reference's own
+ * grid; they are validated the way a caller could observe (threads_per_blk <= 1024) and not used. */
+extern "C" void gpu_hash_search(selem_t *in, loc_t *out, bucket_t *hash_table,
+		int num_elem, int num_thread, int threads_per_blk, cudaStream_t stream)
+{
+	assert(num_elem >= 0);
+	assert(threads_per_blk > 0 && threads_per_blk <= 1024);
+	assert(num_thread > 0);
+	(void)num_thread; (void)threads_per_blk;
+	int rc = gpuhash_search_ex(&g_default_geom, in, out, hash_table, (size_t)num_elem, NULL, (void *)stream);
+	assert(rc >= 0); (void)rc;       /* CUDA errors surface at the caller's next CUDA_SAFE_CALL, as before */
+}
+
+/* reference gpu_hash.cu:521-556 */
+extern "C" void gpu_hash_insert(bucket_t *hash_table, ielem_t **blk_input, int *blk_elem_num,
+		int num_blks, cudaStream_t stream)
+{
+	assert(num_blks >= 0);
+	int rc = gpuhash_insert_ex(&g_default_geom, hash_table, (const void *const *)blk_input, blk_elem_num,
+			num_blks, NULL, 0, (void *)stream);
+	assert(rc >= 0); (void)rc;
+}
+
+/* reference gpu_hash.cu:558-593 */
+extern "C" void gpu_hash_delete(delem_t *in, bucket_t *hash_table, int num_elem, int num_thread,
+		int threads_per_blk, cudaStream_t stream)
+{
+	assert(num_elem >= 0);
+	assert(threads_per_blk > 0 && threads_per_blk <= 1024);
+	(void)num_thread; (void)threads_per_blk;
+	int rc = gpuhash_delete_ex(&g_default_geom, in, hash_table, (size_t)num_elem, NULL, 0, (void *)stream);
+	assert(rc >= 0); (void)rc;
+}
+
+/* reference libgpuhash.h:53-62 (declared, never defined there): delete batch, then insert batch,
+ * stream-ordered so the result equals gpu_hash_delete followed by gpu_hash_insert. */
+extern "C" void gpu_delete_insert(bucket_t *hash_table, delem_t *delete_in, uint32_t num_delete_job,
+		ielem_t **insert_blk_input, int *insert_blk_elem_num, int num_insert_blks,
+		uint32_t num_delete_thread, uint32_t threads_per_blk, cudaStream_t stream)
+{
+	(void)num_delete_thread; (void)threads_per_blk;
+	int rc = gpuhash_delete_ex(&g_default_geom, delete_in, hash_table, (size_t)num_delete_job, NULL, 0, (void *)stream);
+	assert(rc >= 0);
+	rc = gpuhash_insert_ex(&g_default_geom, hash_table, (const void *const *)insert_blk_input,
+			insert_blk_elem_num, num_insert_blks, NULL, 0, (void *)stream);
+	assert(rc >= 0); (void)rc;
+}
+
+/* ------------------------------------------------------------------ plumbing */
+
+extern "C" int gpuhash_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+extern "C" int gpuhash_set_device(int dev) { return (int)cudaSetDevice(dev); }
+
+extern "C" int gpuhash_device_info(int dev, int *sm_count, int *l2_bytes, size_t *free_bytes, size_t *total_bytes)
+{
+	cudaError_t e;
+	if (sm_count && (e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+	if (l2_bytes && (e = cudaDeviceGetAttribute(l2_bytes, cudaDevAttrL2CacheSize, dev)) != cudaSuccess) return (int)e;
+	if (free_bytes || total_bytes) {
+		size_t f = 0, t = 0;
+		if ((e = cudaMemGetInfo(&f, &t)) != cudaSuccess) return (int)e;
+		if (free_bytes) *free_bytes = f;
+		if (total_bytes) *total_bytes = t;
+	}
+	return 0;
+}
+
+extern "C" void *gpuhash_dev_alloc(size_t bytes) { void *p = NULL; return cudaMalloc(&p, bytes) == cudaSuccess ? p : NULL; }
+extern "C" int gpuhash_dev_free(void *p) { return (int)cudaFree(p); }
+extern "C" int gpuhash_dev_memset(void *p, int v, size_t bytes, void *stream)
+{
+	return (int)cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream);
+}
+extern "C" int gpuhash_h2d(void *dst_d, const void *src_h, size_t bytes, void *stream)
+{
+	return (int)cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+extern "C" int gpuhash_d2h(void *dst_h, const void *src_d, size_t bytes, void *stream)
+{
+	return (int)cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+extern "C" void *gpuhash_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
+extern "C" int gpuhash_host_free(void *p) { return (int)cudaFreeHost(p); }
+extern "C" void *gpuhash_stream_create(void) { cudaStream_t s = NULL; return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess ? (void *)s : NULL; }
+extern "C" int gpuhash_stream_destroy(void *s) { return (int)cudaStreamDestroy((cudaStream_t)s); }
+extern "C" int gpuhash_stream_sync(void *s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
+extern "C" int gpuhash_device_sync(void) { return (int)cudaDeviceSynchronize(); }
+extern "C" void *gpuhash_event_create(void) { cudaEvent_t e = NULL; return cudaEventCreate(&e) == cudaSuccess ? (void *)e : NULL; }
+extern "C" int gpuhash_event_destroy(void *e) { return (int)cudaEventDestroy((cudaEvent_t)e); }
+extern "C" int gpuhash_event_record(void *e, void *s) { return (int)cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s); }
+extern "C" int gpuhash_event_elapsed_ms(void *a, void *b, float *ms)
+{
+	cudaError_t e = cudaEventSynchronize((cudaEvent_t)b);
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b);
+}
+extern "C" const char *gpuhash_error_string(int err) { return err < 0 ? "bad argument" : cudaGetErrorString((cudaError_t)err); }
+extern "C" const char *gpuhash_build_info(void)
+{
+	return "megakv_b200 libgpuhash: sm_100a, built " __DATE__ " " __TIME__;
+}
+
+/* ------------------------------------------------------------------ roofline probe */
+
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+	return z ^ (z >> 31);
+}
+
+/* Every thread reads kIlp independent random sectors per round; addresses come from a hash of the
+ * thread index, so the only memory traffic is the gather itself.  The xor of everything read is
+ * stored only if it equals an impossible value, which keeps the loads alive. */
+template <int kIlp, int kMode>
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint32_t *__restrict__ table, uint64_t unit_mask, size_t n, uint32_t seed, uint32_t *sink)
+{
+	uint32_t acc = 0;
+	const size_t stride = (size_t)gridDim.x * blockDim.x * kIlp;
+	for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kIlp; i < n; i += stride) {
+		gh::Row r[kIlp]; gh::Row r2[kIlp];
+#pragma unroll
+		for (int k = 0; k < kIlp; k++) {
+			uint64_t u = mix64((uint64_t)(i + k) * 0x9E3779B97F4A7C15ULL + seed) & unit_mask;
+			const uint32_t *p = kMode == 1 ? table + u * 8 : table + u * 16;
+			r[k] = gh::ld_row_ro(p);
+			if (kMode == 2) r2[k] = gh::ld_row_ro(p + 8);
+		}
+#pragma unroll
+		for (int k = 0; k < kIlp; k++) {
+#pragma unroll
+			for (int l = 0; l < 8; l++) { acc ^= r[k].w[l]; if (kMode == 2) acc ^= r2[k].w[l]; }
+		}
+	}
+	if (acc == 0xDEADBEEFu && seed == 0x12345u) *sink = acc;
+}
+
+template <int kIlp>
+void launch_gather(int mode, const uint32_t *t, uint64_t mask, size_t n, uint32_t seed, uint32_t *sink,
+		unsigned blocks, cudaStream_t s)
+{
+	if (mode == 0)      gather_kernel<kIlp, 0><<<blocks, 256, 0, s>>>(t, mask, n, seed, sink);
+	else if (mode == 1) gather_kernel<kIlp, 1><<<blocks, 256, 0, s>>>(t, mask, n, seed, sink);
+	else                gather_kernel<kIlp, 2><<<blocks, 256, 0, s>>>(t, mask, n, seed, sink);
+}
+
+}  // namespace
+
+extern "C" int gpuhash_roofline_gather(const void *table_d, size_t table_bytes, size_t n, int mode,
+		int loads_per_thread, int iters, float *best_ms, void *stream)
+{
+	if (!table_d || !best_ms || table_bytes < 64 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 2) return -1;
+	cudaStream_t s = (cudaStream_t)stream;
+	uint64_t mask = (mode == 1 ? table_bytes / 32 : table_bytes / 64) - 1;
+	uint32_t *sink = NULL;
+	cudaError_t e = cudaMalloc(&sink, 4);
+	if (e != cudaSuccess) return (int)e;
+	cudaEvent_t a, b;
+	cudaEventCreate(&a); cudaEventCreate(&b);
+	int ilp = loads_per_thread >= 8 ? 8 : loads_per_thread >= 4 ? 4 : loads_per_thread >= 2 ? 2 : 1;
+	size_t blocks = (n + (size_t)256 * ilp - 1) / ((size_t)256 * ilp);
+	if (blocks > 0x7fffffffULL) blocks = 0x7fffffffULL;
+	float best = 1e30f;
+	for (int it = 0; it < iters + 1; it++) {                 /* first launch is warm-up */
+		cudaEventRecord(a, s);
+		uint32_t seed = 1000u + (uint32_t)it;
+		const uint32_t *t = (const uint32_t *)table_d;
+		if (ilp == 8)      launch_gather<8>(mode, t, mask, n, seed, sink, (unsigned)blocks, s);
+		else if (ilp == 4) launch_gather<4>(mode, t, mask, n, seed, sink, (unsigned)blocks, s);
+		else if (ilp == 2) launch_gather<2>(mode, t, mask, n, seed, sink, (unsigned)blocks, s);
+		else               launch_gather<1>(mode, t, mask, n, seed, sink, (unsigned)blocks, s);
+		cudaEventRecord(b, s);
+		if ((e = cudaEventSynchronize(b)) != cudaSuccess) break;
+		float ms = 0; cudaEventElapsedTime(&ms, a, b);
+		if (it > 0 && ms < best) best = ms;
+	}
+	cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+	*best_ms = best;
+	return (int)e;
+}

@@ -1,0 +1,88 @@
+"""Synthetic key streams for the bench and the parity tests (numpy, vectorised).
+
+Keys are 64-bit; a request is derived from a key the way the reference's receiver does it
+(src/mega_recv.c:350,361-362): hash = high 32 bits, sig = low 32 bits.  sig 0 is the table's
+empty marker, so it is mapped to 1 (the reference's unused calc_signature does the same,
+src/mega_common.c:58-59).  loc 0 means "miss" to the consumer (src/mega_send.c:411-414), so
+locations start at 1.
+
+* uniform: key_i = i-th output of splitmix64 started at state `seed`.
+* zipf:    rank r drawn with Gray et al.'s method (the one src/zipf.h:137-183 implements, here
+           with exact pow instead of the reference's approximation), rank -> key_r.
+"""
+import numpy as np
+
+from .hashindex import IEL_DT, SEL_DT
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+
+
+def splitmix64(seed, first, n):
+    """outputs first .. first+n-1 of splitmix64 whose state starts at `seed`"""
+    with np.errstate(over="ignore"):
+        idx = np.arange(first + 1, first + n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * _GOLDEN
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def keys_to_requests(keys, locs=None):
+    keys = np.asarray(keys, dtype=np.uint64)
+    sig = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    sig[sig == 0] = 1
+    hsh = (keys >> np.uint64(32)).astype(np.uint32)
+    sel = np.empty(len(keys), dtype=SEL_DT)
+    sel["sig"], sel["hash"] = sig, hsh
+    if locs is None:
+        return sel
+    iel = np.empty(len(keys), dtype=IEL_DT)
+    iel["sig"], iel["hash"], iel["loc"] = sig, hsh, np.asarray(locs, dtype=np.uint32)
+    return iel, sel
+
+
+def uniform_inserts(seed, first, n):
+    """(ielem[n], selem[n]) for keys first..first+n-1; loc = key index + 1"""
+    return keys_to_requests(splitmix64(seed, first, n), np.arange(first + 1, first + n + 1, dtype=np.uint64))
+
+
+def uniform_queries(seed, population, n, rng):
+    """n searches for keys drawn uniformly from the first `population` keys of the stream"""
+    idx = rng.integers(0, population, size=n, dtype=np.int64)
+    return keys_to_requests(_keys_at(seed, idx)), idx
+
+
+def _keys_at(seed, idx):
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (idx.astype(np.uint64) + np.uint64(1)) * _GOLDEN
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+class Zipf:
+    """Zipf(theta) ranks in [0, n) -- J. Gray et al., SIGMOD'94 (as src/zipf.h)."""
+
+    def __init__(self, n, theta, rng):
+        assert 0.0 < theta < 1.0
+        self.n, self.theta, self.rng = n, theta, rng
+        k = np.arange(1, n + 1, dtype=np.float64)
+        self.zetan = float(np.sum(1.0 / np.power(k, theta)))
+        zeta2 = 1.0 + 0.5 ** theta
+        self.alpha = 1.0 / (1.0 - theta)
+        self.eta = (1.0 - (2.0 / n) ** (1.0 - theta)) / (1.0 - zeta2 / self.zetan)
+        self.thres = 1.0 + 0.5 ** theta
+
+    def ranks(self, m):
+        u = self.rng.random(m)
+        uz = u * self.zetan
+        r = (self.n * np.power(self.eta * (u - 1.0) + 1.0, self.alpha)).astype(np.int64)
+        r[uz < self.thres] = 1
+        r[uz < 1.0] = 0
+        return np.clip(r, 0, self.n - 1)
+
+
+def zipf_queries(seed, population, n, theta, rng):
+    z = Zipf(population, theta, rng)
+    idx = z.ranks(n)
+    return keys_to_requests(_keys_at(seed, idx)), idx
