@@ -277,9 +277,11 @@ delete_kernel(const uint32_t* __restrict__ in /* delem_t[n] as words */, Bucket*
 //                         2-choice: store sig into slot sig & 7, loc untouched (:197-209)
 // A failed CAS means another request changed that slot first: the row is read again and the
 // decision retaken, which is the order "other request, then this one" of a sequential run.
-// kMaxSteps bounds the loop; it is never reached unless > kMaxSteps other requests beat this
-// one to the same slots (counted in ins_gave_up, asserted 0 by the tests).
-constexpr int kMaxSteps = 256;
+// Every failed CAS is another request's success, so the system as a whole always advances
+// (lock-free); kMaxSteps additionally bounds one request's own loop.  Reaching it would need
+// that many other requests to beat this one to the same slots; it is counted in ins_gave_up
+// and the tests assert 0 even under 40 000 requests aimed at 64 buckets.
+constexpr int kMaxSteps = 1 << 16;
 
 __device__ __forceinline__ void insert_one(Bucket* table, const Geom& g,
 		uint32_t sig0, uint32_t hash, uint32_t loc0, Stats* st)

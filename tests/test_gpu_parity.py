@@ -1,0 +1,442 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): search results bit-exact per request; delete hit counts exact; table
+contents exact -- slot for slot where the request order is defined (serial mode, conflict-free batches),
+as a multiset where concurrent requests may legally take each other's slots.
+
+Nothing here reads /root/reference.  The oracle is the checker, never the thing under test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import megakv_b200 as mk
+from megakv_b200 import _native as N
+from oracle import pyoracle as po
+from tests import helpers as H
+from tests.golden import make_golden as MG
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_search(table, sel, prezero=True):
+    sel = np.ascontiguousarray(sel, dtype=mk.SEL_DT)
+    in_d = mk.DeviceBuffer.from_host(sel) if len(sel) else mk.DeviceBuffer(8)
+    out_d = mk.DeviceBuffer(max(8 * len(sel), 8))
+    if prezero:
+        out_d.zero()
+    else:                                                     # the kernel must define every word itself
+        out_d.upload(np.full(2 * max(len(sel), 1), 0xDEADBEEF, dtype=np.uint32))
+    mk.search_ex(table.geom, in_d, out_d, table, len(sel))
+    mk.device_sync()
+    return out_d.download(np.uint32, 2 * len(sel))
+
+
+def gpu_insert(table, iel, flags=0, stats=None):
+    iel = np.ascontiguousarray(iel, dtype=mk.IEL_DT)
+    in_d = mk.DeviceBuffer.from_host(iel) if len(iel) else mk.DeviceBuffer(12)
+    mk.insert_flat_ex(table.geom, table, in_d, len(iel), stats=stats, flags=flags)
+    mk.device_sync()
+
+
+def gpu_delete(table, iel, flags=0):
+    iel = np.ascontiguousarray(iel, dtype=mk.IEL_DT)
+    st = mk.DeviceStats()
+    in_d = mk.DeviceBuffer.from_host(iel) if len(iel) else mk.DeviceBuffer(12)
+    mk.delete_ex(table.geom, in_d, table, len(iel), stats=st, flags=flags)
+    mk.device_sync()
+    return st.read()["del_zeroed"]
+
+
+def table_from_oracle(o):
+    t = mk.DeviceTable(o.mem_p, o.algo)
+    t.upload(o.table)
+    return t
+
+
+# ----------------------------------------------------------------------------- search
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+@pytest.mark.parametrize("mem_p,load", [(16, 0.5), (20, 0.9), (24, 0.3)])
+def test_search_bit_exact_on_oracle_built_tables(gpu, algo, mem_p, load, rng):
+    o = po.Oracle(mem_p, algo)
+    n = int(load * (1 << mem_p) / 8)
+    iel = H.random_requests(rng, n)
+    o.insert(iel)
+    t = table_from_oracle(o)
+    miss = H.random_requests(rng, n // 4 + 1, loc_base=1)
+    sel = np.concatenate([H.to_sel(iel), H.to_sel(miss)])
+    rng.shuffle(sel)
+    want = o.search(sel)
+    assert np.array_equal(gpu_search(t, sel), want)
+    assert np.array_equal(gpu_search(t, sel, prezero=False), want)      # misses are written as 0
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 255, 256, 257, 65535, 65536, 65537, 1000003])
+def test_search_ragged_sizes(gpu, n, rng):
+    o = po.Oracle(18)
+    iel = H.random_requests(rng, 20000)
+    o.insert(iel)
+    t = table_from_oracle(o)
+    sel = H.to_sel(iel)[rng.integers(0, len(iel), n)]
+    assert np.array_equal(gpu_search(t, sel, prezero=False), o.search(sel))
+
+
+@pytest.mark.parametrize("qpt", [1, 2, 4])
+@pytest.mark.parametrize("prefetch", [0, 1])
+def test_search_every_launch_variant(gpu, qpt, prefetch, rng):
+    o = po.Oracle(20)
+    iel = H.random_requests(rng, 100000)
+    o.insert(iel)
+    t = table_from_oracle(o)
+    sel = np.concatenate([H.to_sel(iel), H.to_sel(H.random_requests(rng, 30001))])
+    old = N.Tune(); N.lib().gpuhash_get_tuning(old)
+    try:
+        N.lib().gpuhash_set_tuning(N.Tune(qpt, prefetch, 4))
+        assert np.array_equal(gpu_search(t, sel, prezero=False), o.search(sel))
+    finally:
+        N.lib().gpuhash_set_tuning(old)
+
+
+def test_search_py_search_stream_fixture(gpu, rng):
+    """libgpuhash/test/back/py_search_stream.c:104-129: hit in both buckets for every query."""
+    mem_p = 20
+    o = po.Oracle(mem_p, table=H.fixture_every_bucket_1_to_8(mem_p))
+    t = table_from_oracle(o)
+    sel = np.empty(200000, dtype=mk.SEL_DT)
+    sel["hash"] = rng.integers(0, o.num_buckets, len(sel))
+    sel["sig"] = rng.integers(1, 9, len(sel))
+    got = gpu_search(t, sel)
+    assert np.all(got == 1) and np.array_equal(got, o.search(sel))
+
+
+def test_search_duplicate_signature_behaviour(gpu):
+    """key in both buckets -> both words; same signature twice in a bucket -> highest slot; sig 0 -> empty slots match."""
+    o = po.Oracle(16)
+    tb = o.buckets()
+    sig, h = 0x1234, 5
+    b1, b2 = int(o.bucket1(h)), int(o.bucket2(h, sig))
+    tb[b1, 0, :2] = [9, sig]; tb[b1, 1, :2] = [90, 111]
+    tb[b2, 0, 0] = sig; tb[b2, 1, 0] = 222
+    tb[4, 0, :3] = [0x99, 1, 0x99]; tb[4, 1, :3] = [10, 11, 12]
+    tb[7, 1, :] = np.arange(50, 58)                                      # stale locs in an empty bucket
+    sel = np.array([(sig, h), (sig, b2), (0x99, 4), (0, 7), (0x55 << 16, 4)], dtype=mk.SEL_DT)
+    t = table_from_oracle(o)
+    want = o.search(sel)
+    assert list(want) == [111, 222, 222, 111, 12, 0, 57, 57, 0, 0]
+    assert np.array_equal(gpu_search(t, sel, prezero=False), want)
+
+
+# ----------------------------------------------------------------------------- delete
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+def test_delete_counts_and_table_bytes_exact(gpu, algo, rng):
+    o = po.Oracle(18, algo)
+    iel = H.random_requests(rng, 28000)                                  # ~85 % load
+    o.insert(iel)
+    t = table_from_oracle(o)
+    dele = iel[rng.permutation(len(iel))[:9000]].copy()
+    dele["loc"][::5] += 1                                                # wrong loc: must not delete
+    dele = np.concatenate([dele, H.random_requests(rng, 2000)])          # absent keys
+    want = o.delete(dele)
+    assert gpu_delete(t, dele) == want
+    assert np.array_equal(t.download(np.uint32), o.table)                # stale locs included
+    assert gpu_delete(t, dele) == o.delete(dele) == 0                    # idempotent
+
+
+def test_delete_duplicate_requests_in_one_batch(gpu, rng):
+    """two identical delete requests: the sequential run zeroes once; with the key in both buckets the second
+    request falls through to bucket 2 (gpu_hash.cu:465-468) -- the CAS-based kernel must agree on the count."""
+    o = po.Oracle(16)
+    sig, h = 0x4321, 17
+    b1, b2 = int(o.bucket1(h)), int(o.bucket2(h, sig))
+    tb = o.buckets()
+    tb[b1, 0, 0] = sig; tb[b1, 1, 0] = 5; tb[b2, 0, 3] = sig; tb[b2, 1, 3] = 5
+    iel = H.random_requests(rng, 3000); o.insert(iel)
+    t = table_from_oracle(o)
+    dele = np.concatenate([iel[:500], iel[:500], np.array([(sig, h, 5)] * 2, dtype=mk.IEL_DT)])
+    want = o.delete(dele)
+    assert want == 502
+    assert gpu_delete(t, dele) == want
+    assert np.array_equal(t.download(np.uint32), o.table)
+
+
+# ----------------------------------------------------------------------------- insert, order defined
+
+@pytest.mark.parametrize("name", sorted(MG.CASES))
+def test_golden_sequences_serial_mode_slot_exact(gpu, name):
+    """committed vectors: every search result, delete count and the final table bytes"""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mem_p, algo, steps = MG.unpack_steps(g)
+    t = mk.DeviceTable(mem_p, algo)
+    st = mk.DeviceStats()
+    for i, (op, arr) in enumerate(steps):
+        if op == MG.OP_INSERT:
+            gpu_insert(t, arr, flags=mk.INSERT_SERIAL, stats=st)
+        elif op == MG.OP_DELETE:
+            assert gpu_delete(t, arr, flags=mk.INSERT_SERIAL) == int(g[f"res{i}"][0]), f"step {i}"
+        else:
+            assert np.array_equal(gpu_search(t, arr, prezero=False), g[f"res{i}"]), f"step {i}"
+    assert np.array_equal(t.download(np.uint32), g["table"])
+    s = st.read()
+    got = [s[k] for k in ("ins_skipped", "ins_updated", "ins_placed_b1", "ins_placed_b2", "ins_to_b2",
+                          "ins_displaced", "ins_dropped", "ins_overwritten")]
+    assert got == g["stats"].tolist()
+    assert s["ins_gave_up"] == 0 and s["ins_cas_retry"] == 0
+
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+@pytest.mark.parametrize("load", [0.5, 0.9, 1.05])
+def test_insert_serial_mode_slot_exact_at_any_load(gpu, algo, load, rng):
+    mem_p = 17
+    o = po.Oracle(mem_p, algo)
+    iel = H.random_requests(rng, int(load * (1 << mem_p) / 8))
+    t = mk.DeviceTable(mem_p, algo)
+    st = mk.DeviceStats()
+    for part in np.array_split(iel, 3):
+        o.insert(part)
+        gpu_insert(t, part, flags=mk.INSERT_SERIAL, stats=st)
+    assert np.array_equal(t.download(np.uint32), o.table)
+    s, w = st.read(), o.stats.as_dict()
+    assert (s["ins_to_b2"], s["ins_displaced"], s["ins_dropped"], s["ins_overwritten"]) == \
+           (w["to_b2"], w["displaced"], w["dropped"], w["overwritten"])
+    if algo == po.CUCKOO:
+        assert s["chain_hist"] == w["chain_hist"]
+    sel = H.to_sel(iel)
+    assert np.array_equal(gpu_search(t, sel), o.search(sel))
+
+
+def test_insert_serial_segments_in_block_order(gpu, rng):
+    """legacy layout: 8 segments with device-side counts, some empty (mega_scheduler.c:486-489)"""
+    mem_p = 16
+    o = po.Oracle(mem_p)
+    iel = H.random_requests(rng, 9000)                                   # > 100 % load
+    blocks = mk.split_insert_blocks(iel, 8)
+    blocks[2] = blocks[2][:0]; blocks[7] = blocks[7][:0]
+    o.insert_blocks(blocks)
+    t = mk.DeviceTable(mem_p)
+    segs = mk.InsertSegments(blocks)
+    mk.insert_ex(t.geom, t, segs, flags=mk.INSERT_SERIAL)
+    mk.device_sync()
+    assert np.array_equal(t.download(np.uint32), o.table)
+
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+def test_insert_concurrent_conflict_free_batches_slot_exact(gpu, algo, rng):
+    """no two requests of a batch share a candidate bucket => order cannot matter => identical bytes"""
+    mem_p = 20
+    o = po.Oracle(mem_p, algo)
+    t = mk.DeviceTable(mem_p, algo)
+    total = 0
+    for _ in range(12):
+        batch = H.conflict_free(o, H.random_requests(rng, 6000, loc_base=total + 1))
+        total += len(batch)
+        before = o.stats.to_b2
+        o.insert(batch)
+        assert o.stats.to_b2 == before                                   # stays inside its own buckets
+        gpu_insert(t, batch)
+        assert np.array_equal(t.download(np.uint32), o.table)
+    assert total > 40000
+
+
+# ----------------------------------------------------------------------------- insert, concurrent
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+def test_insert_concurrent_multiset_exact_below_half_load(gpu, algo, rng):
+    """unique keys, load <= 0.5: nothing is dropped or overwritten in any order, so the set of stored
+    (sig, loc) pairs is order-independent; so is every search result as a set."""
+    mem_p = 22
+    o = po.Oracle(mem_p, algo)
+    t = mk.DeviceTable(mem_p, algo)
+    iel = H.random_requests(rng, int(0.5 * (1 << mem_p) / 8))
+    st = mk.DeviceStats()
+    for part in np.array_split(iel, 4):
+        o.insert(part)
+        gpu_insert(t, part, stats=st)
+    assert o.stats.dropped == 0 and o.stats.overwritten == 0
+    got = t.download(np.uint32)
+    assert o.digest(table=got) == o.digest()
+    assert np.array_equal(H.occupied_pairs(o.buckets(got)), H.occupied_pairs(o.buckets()))
+    s = st.read()
+    assert s["ins_gave_up"] == 0 and s["ins_dropped"] == 0 and s["ins_overwritten"] == 0
+    assert s["ins_placed_b1"] + s["ins_placed_b2"] == len(iel)
+    sel = H.to_sel(iel)
+    g, w = gpu_search(t, sel).reshape(-1, 2), o.search(sel).reshape(-1, 2)
+    assert np.array_equal(np.sort(g, axis=1), np.sort(w, axis=1))        # {o0, o1} as a set
+    assert np.all((g == iel["loc"][:, None]).any(axis=1))                # every key findable at its loc
+
+
+def test_insert_legacy_abi_then_search_then_delete(gpu, rng):
+    """the reference's own test, through the three legacy symbols with the reference's launch arguments
+    (insert_test.c:145,173,207): inserted => found, deleted => gone."""
+    mem_p, n = 22, 16384
+    t = mk.DeviceTable(mem_p); t.make_default()
+    o = po.Oracle(mem_p)
+    nb = o.num_buckets
+    out_d = mk.DeviceBuffer(8 * n)
+    for it in range(6):
+        iel = np.empty(n, dtype=mk.IEL_DT)
+        iel["sig"] = rng.integers(1, 2**31, n)
+        iel["hash"] = (np.arange(n) // (n // 8)) * (nb // 8) + rng.integers(0, nb // 8, n)
+        iel["loc"] = rng.integers(1, 2**31, n)
+        in_d = mk.DeviceBuffer.from_host(iel)
+        ptrs = mk.DeviceBuffer.from_host(np.array([in_d.ptr + 12 * k * (n // 8) for k in range(8)], dtype=np.uint64))
+        nums = mk.DeviceBuffer.from_host(np.full(8, n // 8, dtype=np.int32))
+        mk.gpu_hash_insert(t, ptrs, nums, 8)
+        mk.device_sync()
+        sel_d = mk.DeviceBuffer.from_host(H.to_sel(iel))
+        out_d.zero()
+        mk.gpu_hash_search(sel_d, out_d, t, n, 16384, 128)
+        mk.device_sync()
+        out = out_d.download(np.uint32)
+        assert np.all((out[0::2] == iel["loc"]) | (out[1::2] == iel["loc"]))
+        o.insert(iel)
+        assert o.digest(table=t.download(np.uint32)) == o.digest()
+        if it % 2:
+            mk.gpu_hash_delete(in_d, t, n, 16384, 128)
+            mk.device_sync()
+            out_d.zero()
+            mk.gpu_hash_search(sel_d, out_d, t, n, 16384, 128)
+            mk.device_sync()
+            out = out_d.download(np.uint32)
+            assert not np.any((out[0::2] == iel["loc"]) | (out[1::2] == iel["loc"]))
+            o.delete(iel)
+            assert o.digest(table=t.download(np.uint32)) == o.digest()
+
+
+@pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
+def test_insert_concurrent_high_load_invariants(gpu, algo, rng):
+    """90 % load + churn, unconstrained batches: slot placement and which victim is dropped depend on the
+    interleaving, so compare what cannot: pair integrity, conservation, and the oracle's statistics."""
+    mem_p = 20
+    slots = (1 << mem_p) // 8
+    iel = H.random_requests(rng, int(0.9 * slots))
+    o = po.Oracle(mem_p, algo); o.insert(iel)
+    t = mk.DeviceTable(mem_p, algo)
+    st = mk.DeviceStats()
+    for part in np.array_split(iel, 8):
+        gpu_insert(t, part, stats=st)
+    s, w = st.read(), o.stats.as_dict()
+    got = o.buckets(t.download(np.uint32))
+    pairs = H.occupied_pairs(got)
+    legal = np.sort((iel["sig"].astype(np.uint64) << np.uint64(32)) | iel["loc"].astype(np.uint64))
+    if algo == po.CUCKOO:
+        assert np.all(np.isin(pairs, legal))                             # no torn (sig, loc) pair
+        assert len(np.unique(pairs)) == len(pairs)                       # nothing duplicated
+        assert len(pairs) == len(iel) - s["ins_dropped"]                 # conservation
+        assert abs(s["ins_dropped"] - w["dropped"]) <= 0.2 * w["dropped"] + 50
+        assert abs(s["ins_displaced"] - w["displaced"]) <= 0.1 * w["displaced"] + 50
+    else:
+        # 2-choice overwrites keep the old loc: the signature must be legal, the pair need not be
+        assert np.all(np.isin(got[:, 0, :][got[:, 0, :] != 0], iel["sig"]))
+        assert len(pairs) == len(iel) - s["ins_overwritten"]
+        assert abs(s["ins_overwritten"] - w["overwritten"]) <= 0.1 * w["overwritten"] + 50
+    assert s["ins_gave_up"] == 0
+    assert abs(s["ins_to_b2"] - w["to_b2"]) <= 0.05 * w["to_b2"] + 50
+    sel = H.to_sel(iel)
+    found_gpu = (gpu_search(t, sel).reshape(-1, 2) == iel["loc"][:, None]).any(axis=1).sum()
+    found_orc = (o.search(sel).reshape(-1, 2) == iel["loc"][:, None]).any(axis=1).sum()
+    assert abs(int(found_gpu) - int(found_orc)) <= 0.01 * len(iel)
+
+
+def test_insert_same_bucket_contention_keeps_pairs_intact(gpu, rng):
+    """adversarial: 40 000 requests aimed at 64 buckets (and their alternates) in one launch.  Almost
+    everything is evicted or dropped; what survives must be real pairs and no slot may be claimed twice."""
+    mem_p = 16
+    t = mk.DeviceTable(mem_p)
+    iel = H.random_requests(rng, 40000)
+    iel["hash"] = (iel["hash"] & np.uint32(63))
+    st = mk.DeviceStats()
+    gpu_insert(t, iel, stats=st)
+    o = po.Oracle(mem_p)
+    got = o.buckets(t.download(np.uint32))
+    pairs = H.occupied_pairs(got)
+    legal = np.sort((iel["sig"].astype(np.uint64) << np.uint64(32)) | iel["loc"].astype(np.uint64))
+    assert np.all(np.isin(pairs, legal))
+    assert len(np.unique(pairs)) == len(pairs)
+    s = st.read()
+    assert len(pairs) == len(iel) - s["ins_dropped"] - s["ins_gave_up"]
+    assert s["ins_gave_up"] == 0
+
+
+def test_insert_duplicate_keys_in_one_batch(gpu, rng):
+    """zipf-like SET traffic: the same key many times in one launch.  One slot per key, loc = one of the
+    batch's locs for that key (the sequential run keeps the last; a concurrent run keeps some request's)."""
+    mem_p = 18
+    base = H.random_requests(rng, 2000)
+    rep = base[rng.integers(0, 50, 60000)].copy()                        # 50 hot keys
+    rep["loc"] = np.arange(1, len(rep) + 1)
+    batch = np.concatenate([base[50:], rep]); rng.shuffle(batch)
+    t = mk.DeviceTable(mem_p)
+    gpu_insert(t, batch)
+    o = po.Oracle(mem_p); o.insert(batch)
+    got = o.buckets(t.download(np.uint32))
+    assert np.array_equal(np.sort(got[:, 0, :], axis=1), np.sort(o.buckets()[:, 0, :], axis=1))   # same sigs per bucket
+    out = gpu_search(t, H.to_sel(base[:50])).reshape(-1, 2)
+    for k in range(50):
+        locs = rep["loc"][(rep["sig"] == base["sig"][k]) & (rep["hash"] == base["hash"][k])]
+        assert out[k, 0] in locs and out[k, 1] in (0, out[k, 0])    # o1 == o0 iff alt bucket == bucket 1
+
+
+# ----------------------------------------------------------------------------- scheduler-cycle object
+
+def test_index_cycle_matches_oracle_in_reference_order(gpu, rng):
+    """search -> delete -> insert inside one cycle (mega_scheduler.c:392-502): searches of a cycle do not
+    see that cycle's inserts."""
+    mem_p = 20
+    ix = mk.GpuHashIndex(mem_p, workers=2, max_search=1 << 16, max_insert=1 << 15, max_delete=1 << 15)
+    o = po.Oracle(mem_p)
+    live = H.random_requests(rng, 30000)
+    ix.insert(live[:15000]); ix.insert(live[15000:])
+    o.insert(live)
+    loc0 = len(live) + 1
+    for cyc in range(5):
+        fresh = H.random_requests(rng, 3000, loc_base=loc0); loc0 += 3000
+        dele = live[rng.permutation(len(live))[:2000]]
+        sel = np.concatenate([H.to_sel(live[::2]), H.to_sel(fresh)])
+        want = o.search(sel)
+        o.delete(dele); o.insert(fresh)
+        got = ix.cycle(search=sel, delete=dele, insert=fresh, worker=cyc % 2)
+        assert np.array_equal(np.sort(got.reshape(-1, 2), axis=1), np.sort(want.reshape(-1, 2), axis=1))
+        assert not got.reshape(-1, 2)[-3000:].any()                      # this cycle's inserts are not visible yet
+        assert o.digest(table=ix.dump()) == o.digest()
+        live = np.concatenate([live[~np.isin(live["loc"], dele["loc"])], fresh])
+    ix.close()
+
+
+# ----------------------------------------------------------------------------- full size (BASELINE config 2)
+
+def test_full_size_table_properties(gpu, rng):
+    """MEM_P 34 (16 GiB, 2^28 buckets): sizes the oracle cannot hold on the host, so use properties:
+    inserted => found at its loc (both words otherwise 0 or the loc), absent => miss, deleted => gone,
+    and the stats counters balance."""
+    mem_p = 34
+    free = np.zeros(1, dtype=np.uint64); total = np.zeros(1, dtype=np.uint64)
+    import ctypes as C
+    N.check(N.lib().gpuhash_device_info(0, None, None, C.cast(free.ctypes.data, C.POINTER(C.c_size_t)),
+                                        C.cast(total.ctypes.data, C.POINTER(C.c_size_t))))
+    if int(free[0]) < (20 << 30):
+        pytest.skip("needs 20 GiB of free device memory")
+    t = mk.DeviceTable(mem_p)
+    from megakv_b200 import keystream as ks
+    n = 1 << 24                                                          # 16 M keys
+    st = mk.DeviceStats()
+    iel, sel = ks.uniform_inserts(7, 0, n)
+    gpu_insert(t, iel, stats=st)
+    s = st.read()
+    assert s["ins_placed_b1"] + s["ins_placed_b2"] + s["ins_updated"] == n and s["ins_gave_up"] == 0
+    out = gpu_search(t, sel, prezero=False).reshape(-1, 2)
+    assert np.all((out == iel["loc"][:, None]).any(axis=1))
+    assert np.all((out == 0) | (out == iel["loc"][:, None]))
+    _, absent = ks.uniform_inserts(8, 0, 1 << 20)
+    assert not gpu_search(t, absent, prezero=False).any()
+    assert gpu_delete(t, iel[: 1 << 20]) == (1 << 20)
+    out = gpu_search(t, sel[: 1 << 21], prezero=False).reshape(-1, 2)
+    assert not out[: 1 << 20].any() and np.all((out[1 << 20:] == iel["loc"][1 << 20: 1 << 21, None]).any(axis=1))
+    # top-of-table buckets are reachable (64-bit addressing): hash = HASH_MASK
+    hi = np.array([(0x7777, 0x0FFFFFFF, 99), (0x7778, 0xFFFFFFFF, 98)], dtype=mk.IEL_DT)
+    gpu_insert(t, hi)
+    assert list(gpu_search(t, H.to_sel(hi))[[0, 2]]) == [99, 98]
