@@ -2,7 +2,6 @@
 #   make            shared + static library under megakv_b200/lib/
 #   make oracle     CPU oracle (test infrastructure)
 #   make ref        reference kernels in legacy-warp mode into oracle/_ref/ (needs /root/reference)
-#   make tools      sweep / C parity harness
 NVCC     ?= /usr/local/cuda/bin/nvcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 # MEM_P / policy defaults of the three legacy entry points (run-time geometry via gpuhash_ex.h)
@@ -11,7 +10,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Imegakv_b200/csrc $(DEFS
             -Xcompiler -fPIC -Xcompiler -fno-exceptions -Xcompiler -fno-rtti -Xcompiler -Wall
 CSRC     := megakv_b200/csrc
 LIBDIR   := megakv_b200/lib
-OBJS     := $(LIBDIR)/libgpuhash.o $(LIBDIR)/gpuhash_index.o
+OBJS     := $(LIBDIR)/libgpuhash.o $(LIBDIR)/gpuhash_index.o $(LIBDIR)/gpuhash_workload.o
 HDRS     := include/gpu_hash.h include/libgpuhash.h include/gpuhash_ex.h $(wildcard $(CSRC)/*.cuh)
 
 all: $(LIBDIR)/libgpuhash.so $(LIBDIR)/libgpuhash.a
@@ -34,10 +33,7 @@ oracle:
 ref:
 	$(MAKE) -C oracle ref
 
-tools: all
-	$(MAKE) -C tools
-
 clean:
-	rm -rf $(LIBDIR) ; $(MAKE) -C oracle clean ; $(MAKE) -C tools clean
+	rm -rf $(LIBDIR) ; $(MAKE) -C oracle clean
 
-.PHONY: all oracle ref tools clean
+.PHONY: all oracle ref clean

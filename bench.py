@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- batched search/insert Mops/s of the hash-index hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): HASH_CUCKOO, table 2^34 bytes (>> L2), preloaded to load factor 0.25
+(2^29 uniform keys), then K steps; one step = one batch of 65 536 requests = 62 259 searches (95 %, keys drawn
+uniformly from the preloaded population, so every search hits) + 3 277 inserts (5 %, fresh keys).  Per batch:
+one gpu_hash_search-equivalent launch, then one insert launch on the same stream (the reference's in-stream
+order, mega_scheduler.c:392-502); batches go round-robin over S streams like the reference's per-worker streams
+(mega_scheduler.c:276-280).  Every step has its own input/output arrays in HBM (K * 1 MiB >> L2).
+
+  value     whole-job Mops/s with the batches already resident in HBM (CUDA events around the K steps)
+  e2e       the same K steps through the host-buffer C ABI (gpuhash_index_submit): pinned host -> device ->
+            kernels -> pinned host inside the timed region
+  roofline  search kernel only, same batches/streams: algorithmic bytes (8 B request + 2 x 32 B
+            signature sectors + 32 B location sector per hit bucket + 8 B result) / time, against
+            MEASURED_PEAKS.json hbm_gbs; plus one bulk launch and the measured random-32 B-sector ceiling
+  cpu_baseline  oracle (C restatement of the reference's algorithm), one core, bounded sample of the same steps
+
+  --impl reference : the reference's algorithm on the host cores (oracle, all threads) -- same metric/config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 65536
+N_SEARCH = 62259            # 95 %
+N_INSERT = BATCH - N_SEARCH  # 3277 = 5 %
+SEED = 1
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed regions (pynvml, 5 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._run = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "applications_clocks_setting": 0x2}
+        while self._run:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self._run = True
+            self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.nv:
+            self._run = False; self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+
+def cpu_workload(mem_p, preload_log2, steps, threads, log, warm=0):
+    """The same step on the host: oracle table of 2^mem_p bytes preloaded with 2^preload_log2 keys, then `steps`
+    batches of 62 259 searches (all hits) + 3 277 fresh inserts.  Returns (Mops/s, seconds, cores)."""
+    from oracle import pyoracle as po
+    o = po.Oracle(mem_p, po.CUCKOO)
+    pop = 1 << preload_log2
+    t0 = time.time()
+    chunk = 1 << 22
+    for first in range(0, pop, chunk):
+        iel, _ = po.keys(SEED, first, chunk)
+        o.insert_mt(iel, 8)
+    log(f"cpu: preloaded 2^{preload_log2} keys into a 2^{mem_p} B table in {time.time() - t0:.1f} s")
+    rng = np.random.default_rng(7)
+    all_sel = []
+    steps += warm
+    idx = rng.integers(0, pop, size=(steps, N_SEARCH), dtype=np.int64)
+    from megakv_b200 import keystream as ks                     # request derivation only (numpy)
+    for s in range(steps):
+        all_sel.append(ks.keys_to_requests(ks._keys_at(SEED, idx[s])))
+    ins = [po.keys(SEED, pop + s * N_INSERT, N_INSERT)[0] for s in range(steps)]
+    t0 = po.now()
+    for s in range(steps):
+        if s == warm:
+            t0 = po.now()
+        if threads == 1:
+            out = o.search(all_sel[s]); o.insert(ins[s])
+        else:
+            out = o.search_mt(all_sel[s], threads); o.insert_mt(ins[s], threads)
+    dt = po.now() - t0
+    assert ((out[0::2] != 0) | (out[1::2] != 0)).all()
+    return (steps - warm) * BATCH / dt / 1e6, dt, threads
+
+
+def host_mem_p(want):
+    """largest table the host can hold next to everything else (the oracle table lives in host RAM)"""
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 8 << 30
+    p = want
+    while p > 20 and (1 << p) * 1.3 > avail:
+        p -= 1
+    return p
+
+
+def run_reference_arm(args, log):
+    cores = os.cpu_count() or 1
+    mem_p = host_mem_p(args.mem_p)
+    steps = max(1, min(args.steps, 512))
+    warm = max(0, min(args.warmup, 8))
+    val, dt, thr = cpu_workload(mem_p, min(26, mem_p - 7), steps, cores, log, warm=warm)
+    line = {
+        "impl": "reference", "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)",
+        "value": round(val, 3), "unit": "Mops/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": round(1e3 * dt / steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(mem_p, args, note="CPU: oracle (C restatement of gpu_hash.cu), all host threads; "
+                                  f"table 2^{mem_p} B preloaded with 2^{min(26, mem_p - 7)} keys"),
+        "cpu_baseline": {"value": round(val, 3), "unit": "Mops/s", "cores": thr, "kind": "port",
+                         "sample": f"{steps} steps of 65536 requests after {warm} warm-up steps (search_mt + insert_mt), wall clock"},
+        "e2e": {"value": round(val, 3), "unit": "Mops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(mem_p, args, note=None):
+    c = {"workload": f"configs[1]: 1xB200 search-heavy 95/5 GET/SET, uniform keys, HASH_CUCKOO, table 2^{mem_p} bytes, "
+                     f"batch 64K signatures ({N_SEARCH} searches + {N_INSERT} inserts per step)",
+         "mem_p": mem_p, "algo": "HASH_CUCKOO", "load_factor": 0.25, "batch": BATCH,
+         "streams": args.streams, "cuda_graph": bool(args.graph),
+         "cache": "every step has its own request/result arrays (K x 1 MiB > L2) and the table is 16 GiB >> 126 MB L2"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mem-p", type=int, default=34)
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def log(msg):
+        if args.verbose or os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_arm(args, log)
+        return 0
+
+    if world > 1:
+        from megakv_b200 import sharded_bench                     # multi-GPU arm: sharded index + all-to-all routing
+        return sharded_bench.main(args, rank, world, local_rank, log)
+
+    import megakv_b200 as mk
+    from megakv_b200 import _native as N
+    L = mk.lib()
+    mk.require_gpu()
+    N.check(L.gpuhash_set_device(local_rank))
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    mem_p = args.mem_p
+    free, total = C.c_size_t(), C.c_size_t()
+    N.check(L.gpuhash_device_info(local_rank, None, None, C.byref(free), C.byref(total)))
+    while (1 << mem_p) + (8 << 30) > free.value and mem_p > 26:
+        mem_p -= 1
+    S = max(1, min(args.streams, 32))
+    ix = L.gpuhash_index_create(mem_p, N.CUCKOO, S, N_SEARCH, N_INSERT, 1)
+    if not ix:
+        raise mk.GpuHashError("gpuhash_index_create failed")
+    geom = L.gpuhash_index_geom(ix).contents
+    table = L.gpuhash_index_table(ix)
+
+    # ---- preload to load factor 0.25 with device-generated keys
+    pop = (1 << mem_p) // 8 // 4
+    chunk = 1 << 24
+    gen_d = mk.DeviceBuffer(12 * chunk)
+    t0 = time.time()
+    for first in range(0, pop, chunk):
+        n = min(chunk, pop - first)
+        N.check(L.gpuhash_gen_inserts(gen_d.ptr, None, SEED, first, n, None))
+        N.check(L.gpuhash_insert_flat_ex(C.byref(geom), table, gen_d.ptr, n, None, 0, None))
+    N.check(L.gpuhash_device_sync())
+    log(f"preloaded {pop} keys (LF 0.25) into 2^{mem_p} B in {time.time() - t0:.2f} s")
+    gen_d.free()
+
+    # ---- K_d distinct batches resident in HBM
+    kd = min(steps + warm, 4096)
+    search_d = mk.DeviceBuffer(8 * N_SEARCH * kd)
+    out_d = mk.DeviceBuffer(8 * N_SEARCH * kd)
+    insert_d = mk.DeviceBuffer(12 * N_INSERT * kd)
+    N.check(L.gpuhash_gen_queries(search_d.ptr, None, SEED, pop, N_SEARCH * kd, 99, 0.0, 0.0, None))
+    N.check(L.gpuhash_gen_inserts(insert_d.ptr, None, SEED, pop, N_INSERT * kd, None))
+    N.check(L.gpuhash_device_sync())
+
+    def resident(first, count, n_search=N_SEARCH, n_insert=N_INSERT):
+        """`count` steps starting at batch `first` (wrapping inside the kd resident batches); returns seconds"""
+        total_ms, done = 0.0, 0
+        while done < count:
+            b0 = (first + done) % kd
+            c = min(count - done, kd - b0)
+            res = N.BenchResult()
+            N.check(L.gpuhash_bench_resident(C.byref(geom), table,
+                                             search_d.ptr + 8 * N_SEARCH * b0, n_search, out_d.ptr + 8 * N_SEARCH * b0,
+                                             insert_d.ptr + 12 * N_INSERT * b0, n_insert, c, S, args.graph, C.byref(res)),
+                    "gpuhash_bench_resident")
+            total_ms += res.total_ms; done += c
+        return total_ms / 1e3
+
+    sampler = ClockSampler(local_rank)
+    resident(0, warm)                                               # W untimed warm-up steps
+    with sampler:
+        t_val = resident(warm, steps)                               # EXACTLY K timed steps
+    value = steps * BATCH / t_val / 1e6
+    log(f"resident: {steps} steps in {t_val * 1e3:.2f} ms -> {value:.1f} Mops/s")
+
+    # ---- sanity on the timed output: every search of the last timed batch hit (loc != 0 in one of the words)
+    last = (warm + steps - 1) % kd
+    chk = np.empty(2 * N_SEARCH, dtype=np.uint32)
+    N.check(L.gpuhash_d2h(chk.ctypes.data, out_d.ptr + 8 * N_SEARCH * last, chk.nbytes, None)); N.check(L.gpuhash_device_sync())
+    hit_frac = float(((chk[0::2] != 0) | (chk[1::2] != 0)).mean())
+    hits_per_search = float(((chk[0::2] != 0).sum() + (chk[1::2] != 0).sum()) / N_SEARCH)
+    assert hit_frac > 0.999, f"timed searches did not hit: {hit_frac}"
+
+    # ---- roofline: the search kernel alone on the same batches and streams
+    peak, peak_src = peaks()
+    bytes_per_search = 8 + 2 * 32 + 32 * hits_per_search + 8
+    resident(0, min(warm, 50), n_insert=0)
+    with sampler:
+        t_s = resident(warm, steps, n_insert=0)
+    achieved = steps * N_SEARCH * bytes_per_search / t_s / 1e9
+    # one bulk launch (2^24 requests) -- the kernel without launch/ramp effects
+    bulk_n = min(1 << 24, N_SEARCH * kd)
+    res = N.BenchResult()
+    for _ in range(3):
+        N.check(L.gpuhash_bench_resident(C.byref(geom), table, search_d.ptr, bulk_n, out_d.ptr, None, 0, 1, 1, 0, C.byref(res)))
+    bulk_gbs = bulk_n * bytes_per_search / (res.total_ms / 1e3) / 1e9
+    bulk_mops = bulk_n / (res.total_ms / 1e3) / 1e6
+    # measured random-sector ceiling on the same allocation
+    ms = C.c_float()
+    N.check(L.gpuhash_roofline_gather(table, 1 << mem_p, 1 << 27, 0, 4, 3, C.byref(ms), None))
+    sector_rate = (1 << 27) / (ms.value / 1e3)                       # 32 B sectors per second
+    roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None,
+            "kernel": "gh::search_kernel", "peak_source": peak_src, "bytes_per_search": round(bytes_per_search, 2),
+            "launches": steps, "avg_launch_us_effective": round(t_s / steps * 1e6, 3),
+            "bulk_launch": {"requests": bulk_n, "GB/s": round(bulk_gbs, 1), "Mops/s": round(bulk_mops, 1),
+                            "frac": round(bulk_gbs / peak, 4)},
+            "random_sector_probe": {"Gsectors/s": round(sector_rate / 1e9, 2), "GB/s": round(sector_rate * 32 / 1e9, 1),
+                                    "search_frac_of_probe": round(steps * N_SEARCH * (2 + hits_per_search) / t_s / sector_rate, 4),
+                                    "bulk_frac_of_probe": round(bulk_n * (2 + hits_per_search) / (res.total_ms / 1e3) / sector_rate, 4)}}
+
+    # ---- e2e: pinned host buffers through gpuhash_index_submit (H2D + D2H inside the timed region)
+    ke = min(steps, 1024)
+    hs = L.gpuhash_host_alloc(8 * N_SEARCH * ke); ho = L.gpuhash_host_alloc(8 * N_SEARCH * ke); hi = L.gpuhash_host_alloc(12 * N_INSERT * ke)
+    if not (hs and ho and hi):
+        raise mk.GpuHashError("pinned host allocation failed")
+    # fresh insert keys for the e2e pass (after the ones the resident passes used)
+    N.check(L.gpuhash_gen_inserts(insert_d.ptr, None, SEED, pop + N_INSERT * kd, N_INSERT * ke, None))
+    N.check(L.gpuhash_d2h(hs, search_d.ptr, 8 * N_SEARCH * ke, None)); N.check(L.gpuhash_d2h(hi, insert_d.ptr, 12 * N_INSERT * ke, None))
+    N.check(L.gpuhash_device_sync())
+    res = N.BenchResult()
+    N.check(L.gpuhash_bench_e2e(ix, hs, N_SEARCH, ho, hi, N_INSERT, min(ke, max(3, warm)), C.byref(res)))   # warm-up
+    N.check(L.gpuhash_gen_inserts(insert_d.ptr, None, SEED, pop + N_INSERT * (kd + ke), N_INSERT * ke, None))
+    N.check(L.gpuhash_d2h(hi, insert_d.ptr, 12 * N_INSERT * ke, None)); N.check(L.gpuhash_device_sync())
+    t_e, done = 0.0, 0
+    with sampler:
+        w0 = time.time()
+        while done < steps:
+            c = min(ke, steps - done)
+            N.check(L.gpuhash_bench_e2e(ix, hs, N_SEARCH, ho, hi, N_INSERT, c, C.byref(res)), "gpuhash_bench_e2e")
+            t_e += res.total_ms / 1e3; done += c
+        wall_e = time.time() - w0
+    e2e_val = steps * BATCH / t_e / 1e6
+    ho_np = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_uint32)), shape=(2 * N_SEARCH * ke,))
+    assert ((ho_np[0::2] != 0) | (ho_np[1::2] != 0)).mean() > 0.999, "e2e results did not come back"
+    log(f"e2e: {steps} steps in {t_e * 1e3:.2f} ms (wall {wall_e * 1e3:.1f}) -> {e2e_val:.1f} Mops/s")
+
+    # ---- CPU baseline: the oracle on one core, bounded sample of the same steps
+    cpu = None
+    if not args.no_cpu:
+        try:
+            cmem = host_mem_p(mem_p)
+            cval, cdt, _ = cpu_workload(cmem, min(26, cmem - 7), 160, 1, log)
+            cpu = {"value": round(cval, 3), "unit": "Mops/s", "cores": 1, "kind": "port",
+                   "sample": f"160 steps of the same 65536-request batch on a 2^{cmem} B host table preloaded with "
+                             f"2^{min(26, cmem - 7)} keys, oracle/gpuhash_oracle.c, {cdt:.1f} s"}
+        except Exception as e:                                        # never let the checker's environment kill the GPU line
+            cpu = {"value": None, "unit": "Mops/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)",
+        "value": round(value, 1), "unit": "Mops/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": round(t_val / steps * 1e3, 6), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(mem_p, args),
+        "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
+                "d2h_bytes_per_step": 8 * N_SEARCH, "wall_ms": round(wall_e * 1e3, 2), "workers": S},
+        "gpu_launches": 2 * steps,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+        "search_hit_fraction": round(hit_frac, 5),
+    }
+    print(json.dumps(line), flush=True)
+    L.gpuhash_host_free(hs); L.gpuhash_host_free(ho); L.gpuhash_host_free(hi)
+    L.gpuhash_index_destroy(ix)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

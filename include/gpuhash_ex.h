@@ -58,7 +58,8 @@ void   gpuhash_get_default_geom(gpuhash_geom_t *g);
 
 /* ---- launch tuning (process-wide; defaults are what bench.py measures) ---- */
 typedef struct gpuhash_tune_s {
-	int search_qpt;          /* requests per thread: 1, 2 or 4; 0 = choose from batch size */
+	int search_qpt;          /* requests per thread: 1, 2 or 4; 0 = choose from batch size;
+	                            -1 = the 4-lanes-per-request comparison kernel */
 	int search_prefetch_loc; /* 1: L2::64B hint on signature-row loads (pulls the location sector) */
 	int insert_ctas_per_sm;  /* grid of the count-independent insert kernel */
 } gpuhash_tune_t;
@@ -128,6 +129,14 @@ int gpuhash_index_submit(gpuhash_index_t *ix, int worker,
 		const void *delete_in_h, size_t n_delete,
 		const void *insert_in_h, size_t n_insert);
 int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_scheduler.c:504 */
+
+/* ---- synthetic request streams generated on the device (bench tooling; SURVEY.md 8(d) key stream) ----
+ * inserts: keys first..first+n-1 of the splitmix64 stream `seed`, loc = key index + 1; either output may be NULL.
+ * queries: n searches for keys drawn from the first `population` keys, uniformly (theta 0) or Zipf(theta)
+ * with zetan = sum_{k=1..population} k^-theta supplied by the caller; expect_loc_d (optional) gets index + 1. */
+int gpuhash_gen_inserts(void *ielem_d, void *selem_d, uint64_t seed, uint64_t first, size_t n, void *stream);
+int gpuhash_gen_queries(void *selem_d, void *expect_loc_d, uint64_t seed, uint64_t population, size_t n,
+		uint64_t rng_seed, double theta, double zetan, void *stream);
 
 /* ---- timed loops (CUDA events on the launching streams; the Python bench only orchestrates) ---- */
 typedef struct gpuhash_bench_result_s {

@@ -423,3 +423,47 @@ __global__ void delete_serial_kernel(const uint32_t* in, Bucket* table, size_t n
 }
 
 }  // namespace gh
+
+/* ------------------------------------------------------------------ alternative search shape */
+
+namespace gh {
+
+__device__ __forceinline__ uint4 ld_half_row(const uint32_t* p)
+{
+	uint4 v;
+	asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+// Cooperative variant kept for comparison (tools/sweep.py, DESIGN.md "why one thread per request"):
+// four lanes per request -- lanes 0,1 take the two 16 B halves of bucket 1's signature row, lanes
+// 2,3 those of bucket 2 -- 128-bit loads, ballot inside the 4-lane group, the hit lane fetches the
+// location, lane 0 stores the pair.  Same results as search_kernel.
+__global__ void __launch_bounds__(256)
+search_coop4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
+		const Bucket* __restrict__ table, size_t n, Geom g)
+{
+	const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u;
+	const size_t per_iter = ((size_t)gridDim.x * blockDim.x) >> 2;
+	const size_t n_up = (n + 7) & ~(size_t)7;                        // warp-uniform trip count
+	for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < n_up; i += per_iter) {
+		const bool live = i < n;
+		uint2 q = make_uint2(0u, 0u);
+		if (live) q = ld_stream_u2(in + i);
+		const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
+		uint32_t m = 0, loc = 0;
+		if (live) {
+			uint4 v = ld_half_row(table[b].sig + 4 * (sub & 1u));
+			m = (v.x == q.x ? 1u : 0u) | (v.y == q.x ? 2u : 0u) | (v.z == q.x ? 4u : 0u) | (v.w == q.x ? 8u : 0u);
+			if (m) loc = ld_u32_ro(&table[b].loc[4 * (sub & 1u) + (31 - __clz(m))]);
+		}
+		const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 2u) ? 1 : 0));   // higher half wins
+		const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 8u) ? 3 : 2));
+		if (live && sub == 0)
+			st_stream_u2(out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
+	}
+}
+
+}  // namespace gh

@@ -115,6 +115,13 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 	const gh::Bucket *t = (const gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
+	if (qpt < 0) {                                   /* comparison shape: 4 lanes per request */
+		size_t blocks = (n * 4 + 255) / 256;
+		size_t cap = (size_t)sm_count_now() * 64;
+		if (blocks > cap) blocks = cap;
+		gh::search_coop4_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg);
+		return (int)cudaGetLastError();
+	}
 	if (qpt >= 4)      launch_search<4>(in, out, t, n, gg, st, s);
 	else if (qpt >= 2) launch_search<2>(in, out, t, n, gg, st, s);
 	else               launch_search<1>(in, out, t, n, gg, st, s);
