@@ -95,6 +95,8 @@ void *gpuhash_event_create(void);
 int   gpuhash_event_destroy(void *ev);
 int   gpuhash_event_record(void *ev, void *stream);
 int   gpuhash_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
+int   gpuhash_set_l2_fetch_granularity(int bytes);   /* cudaLimitMaxL2FetchGranularity of the current device */
+int   gpuhash_get_l2_fetch_granularity(void);
 const char *gpuhash_error_string(int err);
 const char *gpuhash_build_info(void);
 
@@ -129,6 +131,36 @@ int gpuhash_index_submit(gpuhash_index_t *ix, int worker,
 		const void *delete_in_h, size_t n_delete,
 		const void *insert_in_h, size_t n_insert);
 int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_scheduler.c:504 */
+
+/* ---- sharded index: routing kernels (megakv_b200/csrc/gpuhash_shard.cu; north_star (d)) ----
+ * A logical table of 2^mem_p_total bytes is cut into G = 2^log2_shards contiguous bucket ranges; shard g holds
+ * range g as a local table with gpuhash_geom_init_shard geometry.  The owner of a request is the top log2_shards
+ * bits of (hash & hash_mask_total); both candidate buckets and every eviction target share it (gpu_hash.h:67-69).
+ * Pointer arrays (dst_ptrs, seg_*_ptrs, peer_*_ptrs, staged_ptrs) are HOST arrays of G device pointers, which may
+ * be local or peer (CUDA IPC) addresses.  Regions hold `cap` requests per (source, owner) pair.
+ *   route_scatter    requests -> region d of dst_ptrs by owner d; counts_d[8] = how many went to each owner;
+ *                    perm_d[d*cap + slot] = index of the request in `in` (NULL for insert/delete batches)
+ *   route_publish    fused path: store my counts into every owner's inbox_count[my_rank], then flag[my_rank] = seq
+ *   search_segments  look up num_seg regions (seg_count_d[s] requests each) and store 8 B results to seg_out_ptrs[s];
+ *                    wait_seq != 0: first wait until flags_d[0..num_seg) >= wait_seq (2 s timeout -> *err_d = 1)
+ *   results_publish  fused path: tell every origin its results are stored (flag[my_rank] = seq on each peer)
+ *   route_gather     out[perm[d][j]] = staged[d][j]; optional flag wait like search_segments
+ *   delete_segments  gpu_hash_delete semantics over regions (inserts use gpuhash_insert_ex: counts are ints) */
+int gpuhash_route_scatter(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
+		const void *const *dst_ptrs, uint32_t *counts_d, uint32_t *perm_d, size_t cap, void *stream);
+int gpuhash_route_publish(const uint32_t *counts_d, int log2_shards, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t seq, void *stream);
+int gpuhash_search_segments(const gpuhash_geom_t *g, const void *table_d, int num_seg,
+		const void *const *seg_in_ptrs, const uint32_t *seg_count_d, const void *const *seg_out_ptrs,
+		size_t max_total, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream);
+int gpuhash_results_publish(int log2_shards, int my_rank, const void *const *peer_flag_ptrs, uint32_t seq, void *stream);
+int gpuhash_route_gather(const void *const *staged_ptrs, const uint32_t *perm_d, const uint32_t *counts_d,
+		size_t cap, int log2_shards, void *out_d, size_t n, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream);
+int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, int num_seg, const void *const *seg_in_ptrs,
+		const uint32_t *seg_count_d, size_t max_total, gpuhash_stats_t *stats_d, void *stream);
+int   gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B);      /* cudaIpcGetMemHandle */
+void *gpuhash_ipc_import(const void *handle_64B);                   /* cudaIpcOpenMemHandle, NULL on failure */
+int   gpuhash_ipc_close(void *imported_ptr);
 
 /* ---- synthetic request streams generated on the device (bench tooling; SURVEY.md 8(d) key stream) ----
  * inserts: keys first..first+n-1 of the splitmix64 stream `seed`, loc = key index + 1; either output may be NULL.

@@ -80,6 +80,8 @@ SYMBOLS = {
     "gpuhash_event_destroy": (_i, [_vp]),
     "gpuhash_event_record": (_i, [_vp, _vp]),
     "gpuhash_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
+    "gpuhash_set_l2_fetch_granularity": (_i, [_i]),
+    "gpuhash_get_l2_fetch_granularity": (_i, []),
     "gpuhash_error_string": (C.c_char_p, [_i]),
     "gpuhash_build_info": (C.c_char_p, []),
     "gpuhash_roofline_gather": (_i, [_vp, _sz, _sz, _i, _i, _i, C.POINTER(C.c_float), _vp]),
@@ -95,6 +97,15 @@ SYMBOLS = {
     "gpuhash_index_enable_stats": (_i, [_vp, _i]),
     "gpuhash_index_submit": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gpuhash_index_sync": (_i, [_vp]),
+    "gpuhash_route_scatter": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gpuhash_route_publish": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp]),
+    "gpuhash_search_segments": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
+    "gpuhash_results_publish": (_i, [_i, _i, _vp, C.c_uint32, _vp]),
+    "gpuhash_route_gather": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
+    "gpuhash_delete_segments": (_i, [_gp, _vp, _i, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_ipc_export": (_i, [_vp, _vp]),
+    "gpuhash_ipc_import": (_vp, [_vp]),
+    "gpuhash_ipc_close": (_i, [_vp]),
     "gpuhash_gen_inserts": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, _vp]),
     "gpuhash_gen_queries": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
     "gpuhash_bench_resident": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),

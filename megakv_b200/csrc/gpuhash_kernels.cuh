@@ -155,8 +155,9 @@ __device__ __forceinline__ int first_from(uint32_t mask, int m)
 /* ------------------------------------------------------------------ search */
 
 // gpu_hash.cu:47-72 for one request.  Both buckets are always probed (the early exit at
-// :61-63 is commented out in the reference).  With several matching slots the highest one
-// is reported (the reference lets all matching lanes store to the same word).
+// :61-63 is commented out in the reference).  With several matching slots the LOWEST one is
+// reported: the reference lets all matching lanes store to the same word, and run on a B200 its
+// kernel keeps the lowest lane's store (tests/golden/ref_search_cuckoo_16.npz, dup_* arrays).
 template <bool kPrefetchLoc>
 __device__ __forceinline__ void search_issue(const Bucket* __restrict__ table, const Geom& g,
 		uint2 q /* x = sig, y = hash */, uint32_t& b1, uint32_t& b2, Row& r1, Row& r2)
@@ -173,8 +174,8 @@ __device__ __forceinline__ uint2 search_finish(const Bucket* __restrict__ table,
 	uint32_t m1 = eq_mask(r1, q.x), m2 = eq_mask(r2, q.x);
 	uint2 o = make_uint2(0u, 0u);
 	// the two location loads are independent: issue both before either is consumed
-	const uint32_t* p1 = &table[b1].loc[31 - __clz(m1 | 1u)];
-	const uint32_t* p2 = &table[b2].loc[31 - __clz(m2 | 1u)];
+	const uint32_t* p1 = &table[b1].loc[__ffs(m1 | 0x100u) - 1 & 7];
+	const uint32_t* p2 = &table[b2].loc[__ffs(m2 | 0x100u) - 1 & 7];
 	uint32_t v1 = 0, v2 = 0;
 	if (m1) v1 = ld_u32_ro(p1);
 	if (m2) v2 = ld_u32_ro(p2);
@@ -182,6 +183,7 @@ __device__ __forceinline__ uint2 search_finish(const Bucket* __restrict__ table,
 	return o;
 }
 
+#ifdef GH_DEFINE_KERNELS   /* __global__ definitions: only libgpuhash.cu instantiates them */
 // One thread per request, kQpt requests per thread issued back to back so that each thread
 // keeps 2*kQpt sector reads in flight.  `out` gets both words of every request (0 = miss):
 // the caller's cudaMemset of `out` (mega_scheduler.c:406) is fused away.
@@ -217,6 +219,8 @@ search_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 	}
 }
 
+#endif  /* GH_DEFINE_KERNELS */
+
 /* ------------------------------------------------------------------ delete */
 
 // gpu_hash.cu:454-477 for one request: zero the signature of every slot whose signature AND
@@ -246,6 +250,7 @@ __device__ __forceinline__ int delete_one(Bucket* table, const Geom& g,
 	return delete_in_bucket(table + bucket2(g, hash, sig), sig, loc);
 }
 
+#ifdef GH_DEFINE_KERNELS
 __global__ void __launch_bounds__(256)
 delete_kernel(const uint32_t* __restrict__ in /* delem_t[n] as words */, Bucket* table,
 		size_t n, Geom g, Stats* st)
@@ -258,6 +263,8 @@ delete_kernel(const uint32_t* __restrict__ in /* delem_t[n] as words */, Bucket*
 		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
 	}
 }
+
+#endif  /* GH_DEFINE_KERNELS */
 
 /* ------------------------------------------------------------------ insert */
 
@@ -347,6 +354,7 @@ done:
 	if (st && g.algo == kAlgoCuckoo) atomicAdd(&st->chain_hist[c < 7 ? c : 7], 1ULL);
 }
 
+#ifdef GH_DEFINE_KERNELS
 // The legacy entry point only knows num_blks on the host; segment sizes live in device
 // memory (mega_scheduler.c:493-494).  So the grid is count-independent: every CTA builds
 // the prefix sum of the segment sizes in shared memory and the grid strides over the
@@ -422,8 +430,11 @@ __global__ void delete_serial_kernel(const uint32_t* in, Bucket* table, size_t n
 	}
 }
 
+#endif  /* GH_DEFINE_KERNELS */
+
 }  // namespace gh
 
+#ifdef GH_DEFINE_KERNELS
 /* ------------------------------------------------------------------ alternative search shape */
 
 namespace gh {
@@ -456,14 +467,15 @@ search_coop4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		if (live) {
 			uint4 v = ld_half_row(table[b].sig + 4 * (sub & 1u));
 			m = (v.x == q.x ? 1u : 0u) | (v.y == q.x ? 2u : 0u) | (v.z == q.x ? 4u : 0u) | (v.w == q.x ? 8u : 0u);
-			if (m) loc = ld_u32_ro(&table[b].loc[4 * (sub & 1u) + (31 - __clz(m))]);
+			if (m) loc = ld_u32_ro(&table[b].loc[4 * (sub & 1u) + (__ffs(m) - 1)]);
 		}
 		const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
-		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 2u) ? 1 : 0));   // higher half wins
-		const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 8u) ? 3 : 2));
+		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));   // lower half wins
+		const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
 		if (live && sub == 0)
 			st_stream_u2(out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
 	}
 }
 
 }  // namespace gh
+#endif  /* GH_DEFINE_KERNELS */

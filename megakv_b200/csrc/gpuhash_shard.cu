@@ -1,0 +1,302 @@
+/*
+ * gpuhash_shard.cu -- device side of the sharded index (BASELINE.json north_star (d)).
+ *
+ * The reference is single-GPU (assert(config->scheduler_num == 1), src/mega.c:410; no cudaSetDevice
+ * anywhere).  What makes sharding exact is a property of its hash functions: both candidate buckets of
+ * a key, and every bucket an eviction chain can reach, share the top IBLOCK_P = 3 bits of the bucket
+ * index (BLOCK_HASH_MASK keeps them, gpu_hash.h:67-69, gpu_hash.cu:66-67,334-335).  So G in {2,4,8}
+ * contiguous bucket ranges are closed under search / insert / delete, and shard g can hold its range as
+ * a local table (gpuhash_geom_init_shard) whose results equal the single-table oracle's.
+ *
+ * Per batch, per rank:   scatter requests by owner  ->  exchange  ->  local kernel on what arrived
+ *                        (searches only:)  exchange results back  ->  gather into request order
+ * The exchange is either NCCL (torch.distributed all_to_all, megakv_b200/sharded.py) or -- the fused
+ * path -- the scatter kernel storing straight into the owners' inboxes over NVLink and the lookup kernel
+ * storing results straight into the origin's staging area (peer pointers from CUDA IPC), with
+ * sequence-numbered flags instead of host synchronisation.
+ *
+ * Regions have a fixed capacity `cap` (requests per source per batch), so no prefix sum over the whole
+ * batch is needed: region d of a rank starts at d * cap and a slot is claimed with one shared-memory
+ * atomic per request + one global atomic per (CTA, destination).
+ */
+#include <stdint.h>
+#include <string.h>
+#include <cuda_runtime.h>
+#include "gpuhash_ex.h"
+#include "gpuhash_kernels.cuh"
+
+namespace {
+
+constexpr int kMaxShards = 8;
+
+struct Ptrs { void *p[kMaxShards]; };
+
+/* data another GPU stored into this GPU's memory (or that lives in a peer's): never from L1 */
+__device__ __forceinline__ uint2 ld_u2_sys(const void *p)
+{
+	uint2 v;
+	asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+	uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+
+/* Wait until *flag >= want (flags only grow: they carry the batch sequence number).  System-scope
+ * acquire load: the flag is written by another GPU.  Gives up after `timeout_ns` and reports through
+ * *err so that a dead peer turns into an error code, not a hung box. */
+__device__ __forceinline__ bool wait_flag(const volatile uint32_t *flag, uint32_t want, uint64_t timeout_ns, uint32_t *err)
+{
+	uint64_t t0 = globaltimer_ns();
+	for (;;) {
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if ((int32_t)(v - want) >= 0) return true;
+		if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1u); return false; }
+		__nanosleep(200);
+	}
+}
+
+/* ---- K1: scatter a batch into per-owner regions ------------------------------------------------- */
+template <int kWords>
+__global__ void __launch_bounds__(256)
+route_scatter_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t hash_mask_total, int shift, int G,
+		Ptrs dst, uint32_t *counts /* [G], zero on entry */, uint32_t *perm /* [G][cap] or NULL */, size_t cap)
+{
+	__shared__ uint32_t blk_count[kMaxShards], blk_base[kMaxShards];
+	for (size_t tile = (size_t)blockIdx.x * blockDim.x; tile < n; tile += (size_t)gridDim.x * blockDim.x) {
+		if (threadIdx.x < kMaxShards) blk_count[threadIdx.x] = 0;
+		__syncthreads();
+		const size_t i = tile + threadIdx.x;
+		uint32_t w[kWords]; uint32_t d = 0, rank = 0;
+		if (i < n) {
+#pragma unroll
+			for (int k = 0; k < kWords; k++) w[k] = gh::ld_stream_u32(in + kWords * i + k);
+			d = (w[1] & hash_mask_total) >> shift;                   /* owner = top bits of bucket 1 (== of bucket 2) */
+			rank = atomicAdd(&blk_count[d], 1u);
+		}
+		__syncthreads();
+		if (threadIdx.x < G && blk_count[threadIdx.x])
+			blk_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], blk_count[threadIdx.x]);
+		__syncthreads();
+		if (i < n) {
+			const size_t slot = (size_t)blk_base[d] + rank;          /* < cap as long as cap >= n */
+			uint32_t *q = (uint32_t *)dst.p[d] + kWords * slot;
+#pragma unroll
+			for (int k = 0; k < kWords; k++) q[k] = w[k];            /* plain stores: local HBM or a peer over NVLink */
+			if (perm) perm[(size_t)d * cap + slot] = (uint32_t)i;
+		}
+		__syncthreads();
+	}
+}
+
+/* Publish this rank's per-owner counts to the owners: inbox_count[src=my_rank] on peer d, then the sequence
+ * flag.  One thread per destination; the fence orders the scatter kernel's stores (previous kernel on the
+ * same stream, already complete) and the count before the flag at system scope. */
+__global__ void route_publish_kernel(const uint32_t *counts, int G, int my_rank, Ptrs peer_count /* [G] -> uint32[G] */,
+		Ptrs peer_flag /* [G] -> uint32[G] */, uint32_t seq)
+{
+	int d = threadIdx.x;
+	if (d >= G) return;
+	((volatile uint32_t *)peer_count.p[d])[my_rank] = counts[d];
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)peer_flag.p[d] + my_rank), "r"(seq) : "memory");
+}
+
+/* ---- K2: look up everything that arrived, region by region -------------------------------------- */
+/* seg_count may be written by peers (fused path): then wait_seq != 0 and thread 0 of every CTA first waits
+ * for all G source flags to reach wait_seq. */
+__global__ void __launch_bounds__(256)
+search_segments_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count,
+		Ptrs seg_out, const uint32_t *flags, uint32_t wait_seq, uint32_t *err)
+{
+	__shared__ uint32_t prefix[kMaxShards + 1];
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = 1;
+		if (wait_seq) for (int s = 0; s < G && ok; s++) ok = wait_flag(flags + s, wait_seq, 2000000000ULL, err);
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
+		prefix[G] = acc;
+	}
+	__syncthreads();
+	if (!ok) return;
+	const uint32_t total = prefix[G];
+	int s = 0;
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		while (e >= prefix[s + 1]) s++;
+		const uint32_t j = e - prefix[s];
+		const uint2 q = ld_u2_sys((const uint2 *)seg_in.p[s] + j);
+		uint32_t b1, b2; gh::Row r1, r2;
+		gh::search_issue<false>(table, g, q, b1, b2, r1, r2);
+		const uint2 o = gh::search_finish(table, q, b1, b2, r1, r2);
+		((uint2 *)seg_out.p[s])[j] = o;                               /* local staging or the origin's, over NVLink */
+	}
+}
+
+/* Tell every origin that its results are in place (fused path). */
+__global__ void results_publish_kernel(int G, int my_rank, Ptrs peer_flag, uint32_t seq)
+{
+	int d = threadIdx.x;
+	if (d >= G) return;
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)peer_flag.p[d] + my_rank), "r"(seq) : "memory");
+}
+
+/* ---- K3: results back into request order ---------------------------------------------------------- */
+__global__ void __launch_bounds__(256)
+route_gather_kernel(Ptrs staged /* [G] -> uint2[cap] */, const uint32_t *__restrict__ perm, const uint32_t *counts,
+		size_t cap, int G, uint2 *__restrict__ out, const uint32_t *flags, uint32_t wait_seq, uint32_t *err)
+{
+	__shared__ uint32_t prefix[kMaxShards + 1];
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = 1;
+		if (wait_seq) for (int s = 0; s < G && ok; s++) ok = wait_flag(flags + s, wait_seq, 2000000000ULL, err);
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += counts[s]; }
+		prefix[G] = acc;
+	}
+	__syncthreads();
+	if (!ok) return;
+	const uint32_t total = prefix[G];
+	int s = 0;
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		while (e >= prefix[s + 1]) s++;
+		const uint32_t j = e - prefix[s];
+		const uint2 v = ld_u2_sys((const uint2 *)staged.p[s] + j);
+		gh::st_stream_u2(out + perm[(size_t)s * cap + j], v);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+delete_segments_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, gh::Stats *st)
+{
+	__shared__ uint32_t prefix[kMaxShards + 1];
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += seg_count[s]; }
+		prefix[G] = acc;
+	}
+	__syncthreads();
+	const uint32_t total = prefix[G];
+	int s = 0;
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		while (e >= prefix[s + 1]) s++;
+		const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)(e - prefix[s]);
+		int z = gh::delete_one(table, g, p[0], p[1], p[2]);
+		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+	}
+}
+
+int fill_ptrs(Ptrs &P, const void *const *src, int G)
+{
+	if (G < 1 || G > kMaxShards || !src) return -1;
+	for (int k = 0; k < kMaxShards; k++) P.p[k] = k < G ? (void *)src[k] : nullptr;
+	return 0;
+}
+
+unsigned grid_for(size_t n, int per_sm)
+{
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	size_t blocks = (n + 255) / 256, cap = (size_t)sms * per_sm;
+	if (blocks > cap) blocks = cap;
+	return (unsigned)(blocks ? blocks : 1);
+}
+
+}  // namespace
+
+extern "C" int gpuhash_route_scatter(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total,
+		int log2_shards, const void *const *dst_ptrs /* HOST array [G] of device/peer pointers */,
+		uint32_t *counts_d, uint32_t *perm_d, size_t cap, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs D;
+	if (log2_shards < 0 || log2_shards > 3 || (elem_words != 2 && elem_words != 3) || fill_ptrs(D, dst_ptrs, G) || !counts_d || n > cap) return -1;
+	cudaStream_t s = (cudaStream_t)stream;
+	cudaError_t e = cudaMemsetAsync(counts_d, 0, sizeof(uint32_t) * kMaxShards, s);
+	if (e != cudaSuccess) return (int)e;
+	if (n == 0) return 0;
+	int bits = 0; while ((hash_mask_total >> bits) & 1u) bits++;
+	const int shift = bits - log2_shards;
+	if (shift < 0) return -1;
+	const unsigned blocks = grid_for(n, 16);
+	if (elem_words == 2)
+		route_scatter_kernel<2><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts_d, perm_d, cap);
+	else
+		route_scatter_kernel<3><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts_d, perm_d, cap);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_route_publish(const uint32_t *counts_d, int log2_shards, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t seq, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs C, F;
+	if (fill_ptrs(C, peer_count_ptrs, G) || fill_ptrs(F, peer_flag_ptrs, G)) return -1;
+	route_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts_d, G, my_rank, C, F, seq);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_search_segments(const gpuhash_geom_t *g, const void *table_d, int num_seg,
+		const void *const *seg_in_ptrs, const uint32_t *seg_count_d, const void *const *seg_out_ptrs,
+		size_t max_total, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream)
+{
+	Ptrs I, O;
+	if (!g || fill_ptrs(I, seg_in_ptrs, num_seg) || fill_ptrs(O, seg_out_ptrs, num_seg) || !seg_count_d) return -1;
+	if (wait_seq && (!flags_d || !err_d)) return -1;
+	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo;
+	search_segments_kernel<<<grid_for(max_total, 8), 256, 0, (cudaStream_t)stream>>>((const gh::Bucket *)table_d, gg, num_seg, I,
+			seg_count_d, O, flags_d, wait_seq, err_d);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_results_publish(int log2_shards, int my_rank, const void *const *peer_flag_ptrs, uint32_t seq, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs F;
+	if (fill_ptrs(F, peer_flag_ptrs, G)) return -1;
+	results_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(G, my_rank, F, seq);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_route_gather(const void *const *staged_ptrs, const uint32_t *perm_d, const uint32_t *counts_d,
+		size_t cap, int log2_shards, void *out_d, size_t n, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs S;
+	if (fill_ptrs(S, staged_ptrs, G) || !perm_d || !counts_d || !out_d) return -1;
+	if (wait_seq && (!flags_d || !err_d)) return -1;
+	if (n == 0) return 0;
+	route_gather_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(S, perm_d, counts_d, cap, G, (uint2 *)out_d, flags_d, wait_seq, err_d);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, int num_seg, const void *const *seg_in_ptrs,
+		const uint32_t *seg_count_d, size_t max_total, gpuhash_stats_t *stats_d, void *stream)
+{
+	Ptrs I;
+	if (!g || fill_ptrs(I, seg_in_ptrs, num_seg) || !seg_count_d) return -1;
+	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo;
+	delete_segments_kernel<<<grid_for(max_total, 8), 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, num_seg, I,
+			seg_count_d, (gh::Stats *)stats_d);
+	return (int)cudaGetLastError();
+}
+
+/* ---- CUDA IPC plumbing for the fused path (one process per GPU) ---- */
+extern "C" int gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B)
+{
+	return (int)cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out_64B, dev_ptr);
+}
+extern "C" void *gpuhash_ipc_import(const void *handle_64B)
+{
+	void *p = NULL;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle_64B, sizeof h);
+	return cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? p : NULL;
+}
+extern "C" int gpuhash_ipc_close(void *imported_ptr) { return (int)cudaIpcCloseMemHandle(imported_ptr); }

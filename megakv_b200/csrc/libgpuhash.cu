@@ -16,6 +16,7 @@
 
 #include "libgpuhash.h"
 #include "gpuhash_ex.h"
+#define GH_DEFINE_KERNELS
 #include "gpuhash_kernels.cuh"
 
 static_assert(sizeof(bucket_t) == 64 && sizeof(gh::Bucket) == 64, "bucket_t must be 64 B (gpu_hash.h:79-82)");
@@ -285,6 +286,18 @@ extern "C" int gpuhash_event_elapsed_ms(void *a, void *b, float *ms)
 	if (e != cudaSuccess) return (int)e;
 	return (int)cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b);
 }
+/* DRAM->L2 fetch granularity hint of the current device (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes).
+ * A hash probe wants one 32 B sector per random access; see DESIGN.md "L2 fetch granularity". */
+extern "C" int gpuhash_set_l2_fetch_granularity(int bytes)
+{
+	return (int)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+}
+extern "C" int gpuhash_get_l2_fetch_granularity(void)
+{
+	size_t v = 0;
+	return cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? (int)v : -1;
+}
+
 extern "C" const char *gpuhash_error_string(int err) { return err < 0 ? "bad argument" : cudaGetErrorString((cudaError_t)err); }
 extern "C" const char *gpuhash_build_info(void)
 {

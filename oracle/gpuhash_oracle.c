@@ -53,16 +53,18 @@ uint32_t orc_bucket2(const orc_geom_t *g, uint32_t hash, uint32_t sig)
 /* gpu_hash.cu:47-72.  Every lane whose slot matches stores its loc to the same
  * word; with more than one matching lane the hardware keeps one of the stores.
  * A table built by sequential inserts never holds a non-zero signature twice
- * in a bucket, so this only matters for hand-built tables and for sig == 0;
- * the rule used here (and by the CUDA path) is "highest matching lane". */
+ * in a bucket, so this only matters for hand-built tables and for sig == 0.
+ * The reference's own kernel, run on a B200 (tests/golden/ref_search_cuckoo_16.npz,
+ * dup_* arrays), keeps the LOWEST matching lane's store; that is the rule here
+ * and in the CUDA path. */
 static inline void search_one(const bucket_t *t, const orc_geom_t *g,
 		uint32_t sig, uint32_t hash, uint32_t *o)
 {
 	const bucket_t *b = &t[orc_bucket1(g, hash)];
-	for (int l = 0; l < SLOTS; l++)
+	for (int l = SLOTS - 1; l >= 0; l--)
 		if (b->sig[l] == sig) o[0] = b->loc[l];
 	b = &t[orc_bucket2(g, hash, sig)];        /* always probed, :61-63 is commented out */
-	for (int l = 0; l < SLOTS; l++)
+	for (int l = SLOTS - 1; l >= 0; l--)
 		if (b->sig[l] == sig) o[1] = b->loc[l];
 }
 

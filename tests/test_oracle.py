@@ -238,13 +238,14 @@ def test_all_zero_request_is_skipped_and_zero_sig_writes_loc_into_an_empty_slot(
     assert o.stats.skipped == 1 and not o.buckets().any()
     o.insert(one(0, 3, 9))
     assert o.occupied() == 0 and o.buckets()[3, 1, 0] == 9                       # "match" on the lowest empty slot
-    assert o.search(np.array([(0, 3)], dtype=po.SEL_DT))[0] == 0                 # highest empty slot holds loc 0
+    assert o.search(np.array([(0, 3)], dtype=po.SEL_DT))[0] == 9                 # lowest empty slot now holds loc 9
 
 
-def test_search_highest_matching_lane_wins_on_duplicate_signatures():
+def test_search_lowest_matching_lane_wins_on_duplicate_signatures():
+    """what the reference's kernel does on a B200: tests/golden/ref_search_cuckoo_16.npz (dup_* arrays)"""
     o = po.Oracle(16)
     fill_bucket(o, 4, [0x99, 1, 0x99], [10, 11, 12])
-    assert o.search(np.array([(0x99, 4)], dtype=po.SEL_DT))[0] == 12
+    assert o.search(np.array([(0x99, 4)], dtype=po.SEL_DT))[0] == 10
 
 
 # ----------------------------------------------------------------------------- drivers
