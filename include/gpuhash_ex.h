@@ -30,6 +30,13 @@ extern "C" {
 #define GPUHASH_CUCKOO   0u     /* HASH_CUCKOO   gpu_hash.h:73 */
 #define GPUHASH_2CHOICE  1u     /* HASH_2CHOICE  gpu_hash.h:72 */
 
+/* table layouts.  The caller of the legacy ABI never interprets table bytes (mega_scheduler.c:273-274 only
+ * allocates and zero-fills), so the layout is the library's choice; all-zero == empty in both.
+ *   PAIRS      slot l = 8-byte {sig, loc} at byte 8*l of the 64 B bucket: (sig, loc) changes are one 64-bit CAS
+ *   REFERENCE  bucket_t of gpu_hash.h:79-82 (sig[8] then loc[8]); for callers that memcpy tables in that layout */
+#define GPUHASH_LAYOUT_PAIRS      0u
+#define GPUHASH_LAYOUT_REFERENCE  1u
+
 /* insert flags */
 #define GPUHASH_INSERT_SERIAL  1u   /* one thread, batch order: slot-for-slot equal to a sequential run */
 
@@ -38,6 +45,7 @@ typedef struct gpuhash_geom_s {
 	uint32_t block_mask;    /* BLOCK_HASH_MASK of the LOGICAL table: low bits the alternate bucket may change */
 	uint32_t algo;          /* GPUHASH_CUCKOO | GPUHASH_2CHOICE */
 	uint32_t max_cuckoo;    /* MAX_CUCKOO_NUM (5) */
+	uint32_t layout;        /* GPUHASH_LAYOUT_PAIRS (set by gpuhash_geom_init) | GPUHASH_LAYOUT_REFERENCE */
 } gpuhash_geom_t;
 
 typedef struct gpuhash_stats_s {
@@ -53,6 +61,8 @@ int    gpuhash_geom_init(gpuhash_geom_t *g, int mem_p, unsigned algo);
 /* shard `log2_shards` of a logical 2^mem_p_total-byte table: local table is 2^(mem_p_total-log2_shards) bytes */
 int    gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int log2_shards, unsigned algo);
 size_t gpuhash_table_bytes(const gpuhash_geom_t *g);
+/* in-place rewrite of a table from g->layout to to_layout (async on stream); the caller then sets g->layout */
+int    gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, unsigned to_layout, void *stream);
 void   gpuhash_set_default_geom(const gpuhash_geom_t *g);   /* what the 3 legacy entry points use */
 void   gpuhash_get_default_geom(gpuhash_geom_t *g);
 
@@ -60,7 +70,7 @@ void   gpuhash_get_default_geom(gpuhash_geom_t *g);
 typedef struct gpuhash_tune_s {
 	int search_qpt;          /* requests per thread: 1, 2 or 4; 0 = choose from batch size;
 	                            -1 = the 4-lanes-per-request comparison kernel */
-	int search_prefetch_loc; /* 1: L2::64B hint on signature-row loads (pulls the location sector) */
+	int search_split_mode;   /* REFERENCE layout only: 0 = by table size, 1 = location word on hit only, 2 = whole buckets */
 	int insert_ctas_per_sm;  /* grid of the count-independent insert kernel */
 } gpuhash_tune_t;
 void   gpuhash_set_tuning(const gpuhash_tune_t *t);
@@ -113,13 +123,15 @@ typedef struct gpuhash_index_s gpuhash_index_t;
  * own stream, mega_scheduler.c:276-280); capacities are per worker per cycle (mega.c:136,143-144). */
 gpuhash_index_t *gpuhash_index_create(int mem_p, unsigned algo, int workers,
 		size_t max_search, size_t max_insert, size_t max_delete);
+gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo, unsigned layout, int workers,
+		size_t max_search, size_t max_insert, size_t max_delete);
 void   gpuhash_index_destroy(gpuhash_index_t *ix);
 void  *gpuhash_index_table(gpuhash_index_t *ix);                       /* device pointer */
 const gpuhash_geom_t *gpuhash_index_geom(const gpuhash_index_t *ix);
 void  *gpuhash_index_stream(gpuhash_index_t *ix, int worker);
 int    gpuhash_index_clear(gpuhash_index_t *ix);
-int    gpuhash_index_load(gpuhash_index_t *ix, const void *table_h);   /* reference byte layout */
-int    gpuhash_index_dump(gpuhash_index_t *ix, void *table_h);
+int    gpuhash_index_load(gpuhash_index_t *ix, const void *table_h);   /* host image: reference byte layout, always */
+int    gpuhash_index_dump(gpuhash_index_t *ix, void *table_h);         /* (converted to/from the device layout)     */
 int    gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset);
 int    gpuhash_index_enable_stats(gpuhash_index_t *ix, int on);
 
@@ -158,6 +170,8 @@ int gpuhash_route_gather(const void *const *staged_ptrs, const uint32_t *perm_d,
 		size_t cap, int log2_shards, void *out_d, size_t n, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream);
 int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, int num_seg, const void *const *seg_in_ptrs,
 		const uint32_t *seg_count_d, size_t max_total, gpuhash_stats_t *stats_d, void *stream);
+/* fused path: block the stream until flags_d[0..num) >= want (peers raise them with release semantics); 2 s timeout -> *err_d = 1 */
+int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t want, uint32_t *err_d, void *stream);
 int   gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B);      /* cudaIpcGetMemHandle */
 void *gpuhash_ipc_import(const void *handle_64B);                   /* cudaIpcOpenMemHandle, NULL on failure */
 int   gpuhash_ipc_close(void *imported_ptr);

@@ -10,12 +10,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgpuhash.so")
 
 CUCKOO, TWO_CHOICE = 0, 1
+LAYOUT_PAIRS, LAYOUT_REFERENCE = 0, 1
 INSERT_SERIAL = 1
 
 
 class Geom(C.Structure):                      # gpuhash_geom_t
     _fields_ = [("hash_mask", C.c_uint32), ("block_mask", C.c_uint32),
-                ("algo", C.c_uint32), ("max_cuckoo", C.c_uint32)]
+                ("algo", C.c_uint32), ("max_cuckoo", C.c_uint32), ("layout", C.c_uint32)]
 
 
 class Stats(C.Structure):                     # gpuhash_stats_t
@@ -32,7 +33,7 @@ class Stats(C.Structure):                     # gpuhash_stats_t
 
 
 class Tune(C.Structure):                      # gpuhash_tune_t
-    _fields_ = [("search_qpt", C.c_int), ("search_prefetch_loc", C.c_int), ("insert_ctas_per_sm", C.c_int)]
+    _fields_ = [("search_qpt", C.c_int), ("search_split_mode", C.c_int), ("insert_ctas_per_sm", C.c_int)]
 
 
 class BenchResult(C.Structure):               # gpuhash_bench_result_t
@@ -54,6 +55,7 @@ SYMBOLS = {
     "gpuhash_geom_init": (_i, [_gp, _i, _u]),
     "gpuhash_geom_init_shard": (_i, [_gp, _i, _i, _u]),
     "gpuhash_table_bytes": (_sz, [_gp]),
+    "gpuhash_table_convert": (_i, [_gp, _vp, _u, _vp]),
     "gpuhash_set_default_geom": (None, [_gp]),
     "gpuhash_get_default_geom": (None, [_gp]),
     "gpuhash_set_tuning": (None, [C.POINTER(Tune)]),
@@ -86,6 +88,7 @@ SYMBOLS = {
     "gpuhash_build_info": (C.c_char_p, []),
     "gpuhash_roofline_gather": (_i, [_vp, _sz, _sz, _i, _i, _i, C.POINTER(C.c_float), _vp]),
     "gpuhash_index_create": (_vp, [_i, _u, _i, _sz, _sz, _sz]),
+    "gpuhash_index_create_layout": (_vp, [_i, _u, _u, _i, _sz, _sz, _sz]),
     "gpuhash_index_destroy": (None, [_vp]),
     "gpuhash_index_table": (_vp, [_vp]),
     "gpuhash_index_geom": (_gp, [_vp]),
@@ -103,6 +106,7 @@ SYMBOLS = {
     "gpuhash_results_publish": (_i, [_i, _i, _vp, C.c_uint32, _vp]),
     "gpuhash_route_gather": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_delete_segments": (_i, [_gp, _vp, _i, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_wait_flags": (_i, [_vp, _i, C.c_uint32, _vp, _vp]),
     "gpuhash_ipc_export": (_i, [_vp, _vp]),
     "gpuhash_ipc_import": (_vp, [_vp]),
     "gpuhash_ipc_close": (_i, [_vp]),

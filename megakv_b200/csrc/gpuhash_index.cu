@@ -53,13 +53,23 @@ extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
 	free(ix);
 }
 
+extern "C" gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo, unsigned layout, int workers,
+		size_t max_search, size_t max_insert, size_t max_delete);
+
 extern "C" gpuhash_index_t *gpuhash_index_create(int mem_p, unsigned algo, int workers,
 		size_t max_search, size_t max_insert, size_t max_delete)
 {
-	if (workers < 1 || workers > MAX_WORKERS) return NULL;
+	return gpuhash_index_create_layout(mem_p, algo, GPUHASH_LAYOUT_PAIRS, workers, max_search, max_insert, max_delete);
+}
+
+extern "C" gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo, unsigned layout, int workers,
+		size_t max_search, size_t max_insert, size_t max_delete)
+{
+	if (workers < 1 || workers > MAX_WORKERS || layout > GPUHASH_LAYOUT_REFERENCE) return NULL;
 	gpuhash_index_t *ix = (gpuhash_index_t *)calloc(1, sizeof *ix);
 	if (!ix) return NULL;
 	if (gpuhash_geom_init(&ix->geom, mem_p, algo) != 0) { free(ix); return NULL; }
+	ix->geom.layout = layout;
 	ix->workers = workers;
 	ix->max_search = max_search; ix->max_insert = max_insert; ix->max_delete = max_delete;
 	size_t bytes = gpuhash_table_bytes(&ix->geom);
@@ -93,19 +103,36 @@ extern "C" int gpuhash_index_clear(gpuhash_index_t *ix)
 	return (int)cudaMemset(ix->table, 0, gpuhash_table_bytes(&ix->geom));
 }
 
-/* The table keeps the reference's byte layout (bucket_t[]), so load/dump are plain copies. */
+/* Host images are always in the reference's byte layout (bucket_t[], gpu_hash.h:79-82); the device table
+ * is converted in place on the way in and out when it uses the pair layout. */
 extern "C" int gpuhash_index_load(gpuhash_index_t *ix, const void *table_h)
 {
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) return (int)e;
-	return (int)cudaMemcpy(ix->table, table_h, gpuhash_table_bytes(&ix->geom), cudaMemcpyHostToDevice);
+	e = cudaMemcpy(ix->table, table_h, gpuhash_table_bytes(&ix->geom), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) return (int)e;
+	if (ix->geom.layout != GPUHASH_LAYOUT_REFERENCE) {
+		gpuhash_geom_t as_ref = ix->geom; as_ref.layout = GPUHASH_LAYOUT_REFERENCE;
+		int rc = gpuhash_table_convert(&as_ref, ix->table, ix->geom.layout, NULL);
+		if (rc) return rc;
+	}
+	return (int)cudaDeviceSynchronize();
 }
 
 extern "C" int gpuhash_index_dump(gpuhash_index_t *ix, void *table_h)
 {
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) return (int)e;
-	return (int)cudaMemcpy(table_h, ix->table, gpuhash_table_bytes(&ix->geom), cudaMemcpyDeviceToHost);
+	int rc = gpuhash_table_convert(&ix->geom, ix->table, GPUHASH_LAYOUT_REFERENCE, NULL);
+	if (rc) return rc;
+	e = cudaMemcpy(table_h, ix->table, gpuhash_table_bytes(&ix->geom), cudaMemcpyDeviceToHost);
+	if (ix->geom.layout != GPUHASH_LAYOUT_REFERENCE) {
+		gpuhash_geom_t as_ref = ix->geom; as_ref.layout = GPUHASH_LAYOUT_REFERENCE;
+		rc = gpuhash_table_convert(&as_ref, ix->table, ix->geom.layout, NULL);
+		if (rc) return rc;
+	}
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaDeviceSynchronize();
 }
 
 extern "C" int gpuhash_index_enable_stats(gpuhash_index_t *ix, int on) { ix->stats_on = on != 0; return 0; }

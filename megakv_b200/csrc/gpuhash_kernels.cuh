@@ -2,23 +2,27 @@
  * gpuhash_kernels.cuh -- device side of the B200-native Mega-KV hash index.
  *
  * Written from scratch for sm_100a; it is not a port of the reference kernels
- * (pzrq/megakv libgpuhash/gpu_hash.cu).  What it keeps is the *semantics* of
- * that file, cited per function, and the table bytes (bucket_t, gpu_hash.h:
- * 79-82): a 64 B bucket = one 32 B signature sector + one 32 B location sector.
+ * (pzrq/megakv libgpuhash/gpu_hash.cu).  What it keeps is the *semantics* of that
+ * file, cited per function.
  *
  * Work decomposition (DESIGN.md "Kernels"):
  *   reference: 8 lanes per request, one 4 B load per lane, ballot, __syncthreads
- *   here:      the whole 32 B signature row of a bucket is ONE 256-bit load
- *              (LDG.E.256, new on sm_100), so the "cooperative group per
- *              bucket" collapses into one thread that holds the row in eight
- *              registers and matches it with eight compares.  A warp therefore
- *              has 32 requests x 2 buckets = 64 independent sector reads in
- *              flight per load pair instead of 4, which is what a random-access
- *              HBM-bound kernel needs (Little's law: ~1e5 sectors in flight).
- *   conflicts: the reference arbitrates slot claims with "store, __syncthreads,
- *              re-read" inside one CUDA block and not at all across blocks;
- *              here every claim/eviction is an atomicCAS on the signature word,
- *              which is the linearisation point of the request.
+ *   here:      one thread per request.  A 64 B bucket is two 256-bit loads (LDG.E.256,
+ *              new on sm_100) held in 16 registers and matched with 8 compares, so a
+ *              warp has 32 requests x 2 buckets in flight per load group instead of 4.
+ *
+ * Table layouts (Geom::layout; DESIGN.md "Table layout", profiles/r01_*):
+ *   kLayoutPairs  slot l of a bucket is the 8-byte pair {sig, loc} at byte 8*l.  One 64-bit CAS
+ *                 publishes, updates, evicts or deletes a (sig, loc) pair atomically, so
+ *                 concurrent inserts can never tear a pair.  Default.
+ *   kLayoutSplit  the reference's bytes (bucket_t, gpu_hash.h:79-82): 32 B signature row, then
+ *                 32 B location row.  For callers that memcpy tables in that layout
+ *                 (libgpuhash/test/back/py_search_stream.c:104-121).  Claims/evictions are a CAS
+ *                 on the signature word followed by a store/exchange of the location word: the
+ *                 same two-step publication the reference has, with its (much narrower) window.
+ *   Measured on B200 (ncu, every load flavour): a random 4..32 B read costs a full 128 B line
+ *   of HBM traffic, so both layouts cost the same DRAM bytes per probe (2 lines per search);
+ *   Pairs just never needs the dependent second load for the location.
  */
 #pragma once
 #include <stdint.h>
@@ -29,20 +33,20 @@ namespace gh {
 constexpr int kSlots = 8;                 // ELEM_NUM          gpu_hash.h:49
 constexpr uint32_t kAlgoCuckoo  = 0;      // HASH_CUCKOO       gpu_hash.h:73
 constexpr uint32_t kAlgo2Choice = 1;      // HASH_2CHOICE      gpu_hash.h:72
+constexpr uint32_t kLayoutPairs = 0;
+constexpr uint32_t kLayoutSplit = 1;
 
 struct Geom {                             // == gpuhash_geom_t (gpuhash_ex.h)
 	uint32_t hash_mask;                   // buckets of THIS table - 1   (HASH_MASK, gpu_hash.h:61)
 	uint32_t block_mask;                  // BLOCK_HASH_MASK of the logical table (gpu_hash.h:69)
 	uint32_t algo;
 	uint32_t max_cuckoo;                  // MAX_CUCKOO_NUM    gpu_hash.h:75
+	uint32_t layout;
 };
 
-struct __align__(64) Bucket {             // bucket_t, gpu_hash.h:79-82
-	uint32_t sig[kSlots];
-	uint32_t loc[kSlots];
-};
-
+struct __align__(64) Bucket { uint32_t w[16]; };   // 64 B, stride 64 B in both layouts
 struct __align__(32) Row { uint32_t w[kSlots]; };
+struct Bkt { Row a, b; };                          // a bucket in registers: words 0..7, 8..15
 
 struct Stats {                            // == gpuhash_stats_t (gpuhash_ex.h)
 	unsigned long long ins_skipped, ins_updated, ins_placed_b1, ins_placed_b2, ins_to_b2,
@@ -62,17 +66,6 @@ __device__ __forceinline__ Row ld_row_ro(const uint32_t* p)
 {
 	Row r;
 	asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
-		  "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
-	return r;
-}
-
-// Same, plus an L2 prefetch hint of the enclosing 64 B: pulls the bucket's location sector
-// into L2 together with its signature sector (used by the speculative search variant).
-__device__ __forceinline__ Row ld_row_ro_pf64(const uint32_t* p)
-{
-	Row r;
-	asm volatile("ld.global.L1::no_allocate.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
 		  "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
 	return r;
@@ -102,12 +95,11 @@ __device__ __forceinline__ void st_u32_strong(uint32_t* p, uint32_t v)
 }
 
 // request stream in / result stream out: touched once -> .cs (streaming, evict-first) so they
-// do not displace table sectors from L2 when the table is L2-resident
+// do not displace table lines from L2 when the table is L2-resident
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p)
 {
 	uint2 v;
-	asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];"
-		: "=r"(v.x), "=r"(v.y) : "l"(p));
+	asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
 	return v;
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p)
@@ -118,8 +110,7 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p)
 }
 __device__ __forceinline__ void st_stream_u2(uint2* p, uint2 v)
 {
-	asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};"
-		:: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+	asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 /* ------------------------------------------------------------------ geometry */
@@ -152,49 +143,142 @@ __device__ __forceinline__ int first_from(uint32_t mask, int m)
 	return (__ffs(rot) - 1 + m) & (kSlots - 1);
 }
 
-/* ------------------------------------------------------------------ search */
+/* ---- a whole bucket in registers, read through either layout (all indices compile-time) ---- */
 
-// gpu_hash.cu:47-72 for one request.  Both buckets are always probed (the early exit at
-// :61-63 is commented out in the reference).  With several matching slots the LOWEST one is
-// reported: the reference lets all matching lanes store to the same word, and run on a B200 its
-// kernel keeps the lowest lane's store (tests/golden/ref_search_cuckoo_16.npz, dup_* arrays).
-template <bool kPrefetchLoc>
-__device__ __forceinline__ void search_issue(const Bucket* __restrict__ table, const Geom& g,
-		uint2 q /* x = sig, y = hash */, uint32_t& b1, uint32_t& b2, Row& r1, Row& r2)
+template <bool kPairs, int l> __device__ __forceinline__ uint32_t slot_sig(const Bkt& k)
 {
-	b1 = bucket1(g, q.y);
-	b2 = bucket2(g, q.y, q.x);
-	if (kPrefetchLoc) { r1 = ld_row_ro_pf64(table[b1].sig); r2 = ld_row_ro_pf64(table[b2].sig); }
-	else              { r1 = ld_row_ro(table[b1].sig);      r2 = ld_row_ro(table[b2].sig); }
+	return kPairs ? (l < 4 ? k.a.w[2 * (l & 3)] : k.b.w[2 * (l & 3)]) : k.a.w[l];
+}
+template <bool kPairs, int l> __device__ __forceinline__ uint32_t slot_loc(const Bkt& k)
+{
+	return kPairs ? (l < 4 ? k.a.w[2 * (l & 3) + 1] : k.b.w[2 * (l & 3) + 1]) : k.b.w[l];
 }
 
-__device__ __forceinline__ uint2 search_finish(const Bucket* __restrict__ table, uint2 q,
-		uint32_t b1, uint32_t b2, const Row& r1, const Row& r2)
+template <bool kPairs> __device__ __forceinline__ uint32_t sig_mask(const Bkt& k, uint32_t v)
 {
-	uint32_t m1 = eq_mask(r1, q.x), m2 = eq_mask(r2, q.x);
-	uint2 o = make_uint2(0u, 0u);
-	// the two location loads are independent: issue both before either is consumed
-	const uint32_t* p1 = &table[b1].loc[__ffs(m1 | 0x100u) - 1 & 7];
-	const uint32_t* p2 = &table[b2].loc[__ffs(m2 | 0x100u) - 1 & 7];
-	uint32_t v1 = 0, v2 = 0;
-	if (m1) v1 = ld_u32_ro(p1);
-	if (m2) v2 = ld_u32_ro(p2);
-	o.x = v1; o.y = v2;
-	return o;
+	return (slot_sig<kPairs, 0>(k) == v ? 1u : 0u)   | (slot_sig<kPairs, 1>(k) == v ? 2u : 0u)
+	     | (slot_sig<kPairs, 2>(k) == v ? 4u : 0u)   | (slot_sig<kPairs, 3>(k) == v ? 8u : 0u)
+	     | (slot_sig<kPairs, 4>(k) == v ? 16u : 0u)  | (slot_sig<kPairs, 5>(k) == v ? 32u : 0u)
+	     | (slot_sig<kPairs, 6>(k) == v ? 64u : 0u)  | (slot_sig<kPairs, 7>(k) == v ? 128u : 0u);
+}
+template <bool kPairs> __device__ __forceinline__ uint32_t loc_mask(const Bkt& k, uint32_t v)
+{
+	return (slot_loc<kPairs, 0>(k) == v ? 1u : 0u)   | (slot_loc<kPairs, 1>(k) == v ? 2u : 0u)
+	     | (slot_loc<kPairs, 2>(k) == v ? 4u : 0u)   | (slot_loc<kPairs, 3>(k) == v ? 8u : 0u)
+	     | (slot_loc<kPairs, 4>(k) == v ? 16u : 0u)  | (slot_loc<kPairs, 5>(k) == v ? 32u : 0u)
+	     | (slot_loc<kPairs, 6>(k) == v ? 64u : 0u)  | (slot_loc<kPairs, 7>(k) == v ? 128u : 0u);
+}
+// sig / loc of slot l for a run-time l: a select chain, no local-memory indexing
+template <bool kPairs> __device__ __forceinline__ uint32_t sig_at(const Bkt& k, int l)
+{
+	uint32_t v = slot_sig<kPairs, 0>(k);
+	if (l == 1) v = slot_sig<kPairs, 1>(k);
+	if (l == 2) v = slot_sig<kPairs, 2>(k);
+	if (l == 3) v = slot_sig<kPairs, 3>(k);
+	if (l == 4) v = slot_sig<kPairs, 4>(k);
+	if (l == 5) v = slot_sig<kPairs, 5>(k);
+	if (l == 6) v = slot_sig<kPairs, 6>(k);
+	if (l == 7) v = slot_sig<kPairs, 7>(k);
+	return v;
+}
+template <bool kPairs> __device__ __forceinline__ uint32_t loc_at(const Bkt& k, int l)
+{
+	uint32_t v = slot_loc<kPairs, 0>(k);
+	if (l == 1) v = slot_loc<kPairs, 1>(k);
+	if (l == 2) v = slot_loc<kPairs, 2>(k);
+	if (l == 3) v = slot_loc<kPairs, 3>(k);
+	if (l == 4) v = slot_loc<kPairs, 4>(k);
+	if (l == 5) v = slot_loc<kPairs, 5>(k);
+	if (l == 6) v = slot_loc<kPairs, 6>(k);
+	if (l == 7) v = slot_loc<kPairs, 7>(k);
+	return v;
+}
+
+__device__ __forceinline__ Bkt ld_bucket_ro(const Bucket* b)
+{
+	Bkt k; k.a = ld_row_ro(b->w); k.b = ld_row_ro(b->w + 8); return k;
+}
+__device__ __forceinline__ Bkt ld_bucket_strong(const Bucket* b)
+{
+	Bkt k; k.a = ld_row_strong(b->w); k.b = ld_row_strong(b->w + 8); return k;
+}
+
+/* ------------------------------------------------------------------ search */
+
+// gpu_hash.cu:47-72 for one request.  Both buckets are always probed (the early exit at :61-63
+// is commented out in the reference).  With several matching slots the LOWEST one is reported:
+// the reference lets all matching lanes store to the same word, and run on a B200 its kernel
+// keeps the lowest lane's store (tests/golden/ref_search_cuckoo_16.npz, dup_* arrays).
+//
+// kSearchPairs       Pairs layout, whole buckets (4 x LDG.256, no dependent load)
+// kSearchSplitWhole  Split layout, whole buckets (signature AND location row up front; same DRAM lines)
+// kSearchSplitLazy   Split layout, signature rows first, location word only on a hit (fewest L2
+//                    sectors: chosen when the table fits in L2, where sectors -- not DRAM lines --
+//                    are the cost)
+constexpr int kSearchPairs = 0, kSearchSplitWhole = 1, kSearchSplitLazy = 2;
+
+template <int kMode> struct Probe { uint32_t b1, b2; Bkt k1, k2; };
+template <> struct Probe<kSearchSplitLazy> { uint32_t b1, b2; Row r1, r2; };
+
+template <int kMode>
+__device__ __forceinline__ void search_issue(const Bucket* __restrict__ table, const Geom& g,
+		uint2 q /* x = sig, y = hash */, Probe<kMode>& p)
+{
+	p.b1 = bucket1(g, q.y);
+	p.b2 = bucket2(g, q.y, q.x);
+	if constexpr (kMode == kSearchSplitLazy) {
+		p.r1 = ld_row_ro(table[p.b1].w); p.r2 = ld_row_ro(table[p.b2].w);
+	} else {
+		p.k1 = ld_bucket_ro(table + p.b1); p.k2 = ld_bucket_ro(table + p.b2);
+	}
+}
+
+template <int kMode>
+__device__ __forceinline__ uint2 search_finish(const Bucket* __restrict__ table, uint2 q,
+		const Probe<kMode>& p, uint32_t& hit1, uint32_t& hit2)
+{
+	if constexpr (kMode == kSearchSplitLazy) {
+		hit1 = eq_mask(p.r1, q.x); hit2 = eq_mask(p.r2, q.x);
+		// the two location loads are independent: issue both before either is consumed
+		const uint32_t* p1 = &table[p.b1].w[8 + ((__ffs(hit1 | 0x100u) - 1) & 7)];
+		const uint32_t* p2 = &table[p.b2].w[8 + ((__ffs(hit2 | 0x100u) - 1) & 7)];
+		uint32_t v1 = 0, v2 = 0;
+		if (hit1) v1 = ld_u32_ro(p1);
+		if (hit2) v2 = ld_u32_ro(p2);
+		return make_uint2(v1, v2);
+	} else {
+		constexpr bool kPairs = kMode == kSearchPairs;
+		hit1 = sig_mask<kPairs>(p.k1, q.x); hit2 = sig_mask<kPairs>(p.k2, q.x);
+		uint32_t v1 = hit1 ? loc_at<kPairs>(p.k1, __ffs(hit1) - 1) : 0u;
+		uint32_t v2 = hit2 ? loc_at<kPairs>(p.k2, __ffs(hit2) - 1) : 0u;
+		return make_uint2(v1, v2);
+	}
+}
+
+// run-time layout dispatch for callers outside libgpuhash.cu (the sharded lookup kernel)
+__device__ __forceinline__ uint2 search_one(const Bucket* __restrict__ table, const Geom& g, uint2 q)
+{
+	uint32_t h1, h2;
+	if (g.layout == kLayoutPairs) {
+		Probe<kSearchPairs> p; search_issue<kSearchPairs>(table, g, q, p);
+		return search_finish<kSearchPairs>(table, q, p, h1, h2);
+	}
+	Probe<kSearchSplitWhole> p; search_issue<kSearchSplitWhole>(table, g, q, p);
+	return search_finish<kSearchSplitWhole>(table, q, p, h1, h2);
 }
 
 #ifdef GH_DEFINE_KERNELS   /* __global__ definitions: only libgpuhash.cu instantiates them */
 // One thread per request, kQpt requests per thread issued back to back so that each thread
-// keeps 2*kQpt sector reads in flight.  `out` gets both words of every request (0 = miss):
-// the caller's cudaMemset of `out` (mega_scheduler.c:406) is fused away.
-template <int kQpt, bool kPrefetchLoc>
+// keeps 2*kQpt (lazy) or 4*kQpt (whole) 32 B reads in flight.  `out` gets both words of every
+// request (0 = miss): the caller's cudaMemset of `out` (mega_scheduler.c:406) is fused away.
+template <int kQpt, int kMode>
 __global__ void __launch_bounds__(256)
 search_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		const Bucket* __restrict__ table, size_t n, Geom g, Stats* st)
 {
 	const size_t tile = (size_t)blockDim.x * kQpt;
 	for (size_t base = (size_t)blockIdx.x * tile; base < n; base += (size_t)gridDim.x * tile) {
-		uint2 q[kQpt]; uint32_t b1[kQpt], b2[kQpt]; Row r1[kQpt], r2[kQpt];
+		uint2 q[kQpt]; Probe<kMode> p[kQpt];
 		bool live[kQpt];
 #pragma unroll
 		for (int k = 0; k < kQpt; k++) {
@@ -204,92 +288,85 @@ search_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		}
 #pragma unroll
 		for (int k = 0; k < kQpt; k++)
-			if (live[k]) search_issue<kPrefetchLoc>(table, g, q[k], b1[k], b2[k], r1[k], r2[k]);
+			if (live[k]) search_issue<kMode>(table, g, q[k], p[k]);
 #pragma unroll
 		for (int k = 0; k < kQpt; k++) {
 			if (!live[k]) continue;
 			size_t i = base + (size_t)k * blockDim.x + threadIdx.x;
-			uint2 o = search_finish(table, q[k], b1[k], b2[k], r1[k], r2[k]);
+			uint32_t h1, h2;
+			uint2 o = search_finish<kMode>(table, q[k], p[k], h1, h2);
 			st_stream_u2(out + i, o);
 			if (st) {
-				if (eq_mask(r1[k], q[k].x)) atomicAdd(&st->search_hits_b1, 1ULL);
-				if (eq_mask(r2[k], q[k].x)) atomicAdd(&st->search_hits_b2, 1ULL);
+				if (h1) atomicAdd(&st->search_hits_b1, 1ULL);
+				if (h2) atomicAdd(&st->search_hits_b2, 1ULL);
 			}
 		}
 	}
 }
-
 #endif  /* GH_DEFINE_KERNELS */
 
 /* ------------------------------------------------------------------ delete */
 
 // gpu_hash.cu:454-477 for one request: zero the signature of every slot whose signature AND
-// location match; visit bucket 2 only if this request zeroed nothing in bucket 1.  The
-// zeroing is a CAS(sig -> 0), so two identical requests of one batch behave like the
-// sequential run: the first zeroes, the second sees a miss and goes on to bucket 2.
+// location match (the location word stays); visit bucket 2 only if this request zeroed nothing
+// in bucket 1 (:465-468).  The zeroing is a CAS, so two identical requests of one batch behave
+// like the sequential run: the first zeroes, the second sees a miss and goes on to bucket 2.
+template <bool kPairs>
 __device__ __forceinline__ int delete_in_bucket(Bucket* bk, uint32_t sig, uint32_t loc)
 {
-	Row s = ld_row_strong(bk->sig);
-	uint32_t m = eq_mask(s, sig);
-	if (!m) return 0;
-	Row l = ld_row_strong(bk->loc);
-	m &= eq_mask(l, loc);
+	Bkt k = ld_bucket_strong(bk);
+	uint32_t m = sig_mask<kPairs>(k, sig) & loc_mask<kPairs>(k, loc);
 	int zeroed = 0;
 	while (m) {
-		int slot = __ffs(m) - 1; m &= m - 1;
-		if (atomicCAS(&bk->sig[slot], sig, 0u) == sig) zeroed++;
+		int l = __ffs(m) - 1; m &= m - 1;
+		if (kPairs) {
+			unsigned long long expect = ((unsigned long long)loc << 32) | sig;
+			unsigned long long* slot = (unsigned long long*)&bk->w[2 * l];
+			if (atomicCAS(slot, expect, (unsigned long long)loc << 32) == expect) zeroed++;
+		} else {
+			if (atomicCAS(&bk->w[l], sig, 0u) == sig) zeroed++;
+		}
 	}
 	return zeroed;
 }
 
+template <bool kPairs>
 __device__ __forceinline__ int delete_one(Bucket* table, const Geom& g,
 		uint32_t sig, uint32_t hash, uint32_t loc)
 {
-	int z = delete_in_bucket(table + bucket1(g, hash), sig, loc);
-	if (z) return z;                                                   // :465-468
-	return delete_in_bucket(table + bucket2(g, hash, sig), sig, loc);
+	int z = delete_in_bucket<kPairs>(table + bucket1(g, hash), sig, loc);
+	if (z) return z;
+	return delete_in_bucket<kPairs>(table + bucket2(g, hash, sig), sig, loc);
 }
-
-#ifdef GH_DEFINE_KERNELS
-__global__ void __launch_bounds__(256)
-delete_kernel(const uint32_t* __restrict__ in /* delem_t[n] as words */, Bucket* table,
-		size_t n, Geom g, Stats* st)
-{
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-			i += (size_t)gridDim.x * blockDim.x) {
-		uint32_t sig = ld_stream_u32(in + 3 * i), hash = ld_stream_u32(in + 3 * i + 1),
-		         loc = ld_stream_u32(in + 3 * i + 2);
-		int z = delete_one(table, g, sig, hash, loc);
-		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
-	}
-}
-
-#endif  /* GH_DEFINE_KERNELS */
 
 /* ------------------------------------------------------------------ insert */
 
 #define GH_COUNT(field) do { if (st) atomicAdd(&st->field, 1ULL); } while (0)
 
-// gpu_hash.cu:256-430 (cuckoo) and :97-226 (2-choice) for one request, as a bounded
-// lock-free loop.  One iteration = "read the signature row of the current bucket, decide,
-// commit with one CAS":
-//   signature present  -> store loc (update in place)             :277-287, 339-349
-//   empty slot         -> CAS(sig[l]: 0 -> sig), then store loc   :303-327, 351-395
-//                         l = first empty from the major location (sig0 & 7)
-//   bucket 1 full      -> go to the alternate bucket              :330-336
-//   alternate full     -> cuckoo:  victim slot sig0 & 7; CAS(sig[l]: victim -> sig),
-//                                  exchange loc, carry the victim on -- with the REQUEST's
-//                                  hash, never the victim's (:334-335, 403-404) -- at most
-//                                  max_cuckoo times, then overwrite without re-homing (:414-422)
-//                         2-choice: store sig into slot sig & 7, loc untouched (:197-209)
-// A failed CAS means another request changed that slot first: the row is read again and the
-// decision retaken, which is the order "other request, then this one" of a sequential run.
+// gpu_hash.cu:256-430 (cuckoo) and :97-226 (2-choice) for one request, as a bounded lock-free
+// loop.  One iteration = "read the current bucket, decide, commit with one CAS":
+//   signature present  -> new location (update in place)              :277-287, 339-349
+//   empty slot         -> claim it; slot = first empty from the major location sig0 & 7
+//                                                                      :303-327, 351-395
+//   bucket 1 full      -> go to the alternate bucket                   :330-336
+//   alternate full     -> cuckoo:  victim slot sig0 & 7 is replaced and the victim carried on --
+//                                  with the REQUEST's hash, never the victim's (:334-335,
+//                                  403-404) -- at most max_cuckoo times, then the victim is
+//                                  overwritten without re-homing (:414-422)
+//                         2-choice: signature stored into slot sig & 7, location untouched (:197-209)
+// Pairs layout: every commit is ONE 64-bit CAS on the {sig, loc} slot, expected value = what
+// this thread read.  A failed CAS means another request changed that slot first: the bucket is
+// read again and the decision retaken -- the order "other request, then this one" of a
+// sequential run.  The table therefore always equals SOME sequential execution of the batch.
+// Split layout: the CAS is on the signature word; the location follows with a store (claim,
+// update) or an exchange (eviction).  Two requests that take the same slot within that gap can
+// pair a signature with the other's location -- the reference's own publication window.
 // Every failed CAS is another request's success, so the system as a whole always advances
-// (lock-free); kMaxSteps additionally bounds one request's own loop.  Reaching it would need
-// that many other requests to beat this one to the same slots; it is counted in ins_gave_up
-// and the tests assert 0 even under 40 000 requests aimed at 64 buckets.
+// (lock-free); kMaxSteps additionally bounds one request's own loop (counted in ins_gave_up,
+// asserted 0 by the tests even with 40 000 requests aimed at 64 buckets).
 constexpr int kMaxSteps = 1 << 16;
 
+template <bool kPairs>
 __device__ __forceinline__ void insert_one(Bucket* table, const Geom& g,
 		uint32_t sig0, uint32_t hash, uint32_t loc0, Stats* st)
 {
@@ -303,25 +380,41 @@ __device__ __forceinline__ void insert_one(Bucket* table, const Geom& g,
 
 	for (int step = 0; step < kMaxSteps; step++) {
 		Bucket* bk = table + b;
-		Row r = ld_row_strong(bk->sig);
-		uint32_t hit = eq_mask(r, sig);
-		if (hit) {                                                   // update in place
-			st_u32_strong(&bk->loc[__ffs(hit) - 1], loc);
+		Bkt k;
+		if (kPairs) k = ld_bucket_strong(bk);
+		else { k.a = ld_row_strong(bk->w); k.b = k.a; }              // Split: the signature row is enough
+		const uint32_t hit = sig_mask<kPairs>(k, sig);
+		if (hit) {                                                   // update in place, lowest slot
+			const int l = __ffs(hit) - 1;
+			if (kPairs) {
+				unsigned long long expect = ((unsigned long long)loc_at<true>(k, l) << 32) | sig;
+				unsigned long long want = ((unsigned long long)loc << 32) | sig;
+				if (expect != want && atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) != expect) {
+					GH_COUNT(ins_cas_retry); continue;
+				}
+			} else {
+				st_u32_strong(&bk->w[8 + l], loc);
+			}
 			GH_COUNT(ins_updated);
 			goto done;
 		}
-		uint32_t empty = eq_mask(r, 0u);
+		const uint32_t empty = sig_mask<kPairs>(k, 0u);
 		if (empty) {
-			int l = first_from(empty, major);
-			uint32_t old = atomicCAS(&bk->sig[l], 0u, sig);
-			if (old == 0u || old == sig) {                           // claimed, or a twin claimed it
-				st_u32_strong(&bk->loc[l], loc);
-				if (old == 0u) { if (alt) GH_COUNT(ins_placed_b2); else GH_COUNT(ins_placed_b1); }
-				else GH_COUNT(ins_updated);
-				goto done;
+			const int l = first_from(empty, major);
+			if (kPairs) {
+				unsigned long long expect = (unsigned long long)loc_at<true>(k, l) << 32;   // {0, stale loc}
+				unsigned long long want = ((unsigned long long)loc << 32) | sig;
+				if (atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) != expect) {
+					GH_COUNT(ins_cas_retry); continue;
+				}
+			} else {
+				const uint32_t old = atomicCAS(&bk->w[l], 0u, sig);
+				if (old != 0u && old != sig) { GH_COUNT(ins_cas_retry); continue; }
+				st_u32_strong(&bk->w[8 + l], loc);
+				if (old == sig) { GH_COUNT(ins_updated); goto done; }   // a twin claimed it first
 			}
-			GH_COUNT(ins_cas_retry);
-			continue;                                                // slot taken: look again
+			if (alt) GH_COUNT(ins_placed_b2); else GH_COUNT(ins_placed_b1);
+			goto done;
 		}
 		if (!alt) {                                                  // bucket 1 full
 			alt = true;
@@ -331,14 +424,32 @@ __device__ __forceinline__ void insert_one(Bucket* table, const Geom& g,
 		}
 		// alternate bucket full
 		const int l = (int)(sig0 & (kSlots - 1));                    // elem->sig :200, 360
-		if (g.algo == kAlgo2Choice) {
-			st_u32_strong(&bk->sig[l], sig);                         // loc NOT written :197-209
+		const uint32_t vsig = sig_at<kPairs>(k, l);
+		if (g.algo == kAlgo2Choice) {                                // signature only :197-209
+			if (kPairs) {
+				const unsigned long long vloc = loc_at<true>(k, l);
+				unsigned long long expect = (vloc << 32) | vsig, want = (vloc << 32) | sig;
+				if (atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) != expect) {
+					GH_COUNT(ins_cas_retry); continue;
+				}
+			} else {
+				st_u32_strong(&bk->w[l], sig);
+			}
 			GH_COUNT(ins_overwritten);
 			goto done;
 		}
-		uint32_t vsig = r.w[l];
-		if (atomicCAS(&bk->sig[l], vsig, sig) != vsig) { GH_COUNT(ins_cas_retry); continue; }
-		uint32_t vloc = atomicExch(&bk->loc[l], loc);
+		uint32_t vloc;
+		if (kPairs) {
+			vloc = loc_at<true>(k, l);
+			unsigned long long expect = ((unsigned long long)vloc << 32) | vsig;
+			unsigned long long want = ((unsigned long long)loc << 32) | sig;
+			if (atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) != expect) {
+				GH_COUNT(ins_cas_retry); continue;
+			}
+		} else {
+			if (atomicCAS(&bk->w[l], vsig, sig) != vsig) { GH_COUNT(ins_cas_retry); continue; }
+			vloc = atomicExch(&bk->w[8 + l], loc);
+		}
 		if (c < g.max_cuckoo) {                                      // :361-365, 397-405
 			c++;
 			GH_COUNT(ins_displaced);
@@ -355,12 +466,27 @@ done:
 }
 
 #ifdef GH_DEFINE_KERNELS
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+delete_kernel(const uint32_t* __restrict__ in /* delem_t[n] as words */, Bucket* table,
+		size_t n, Geom g, Stats* st)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+			i += (size_t)gridDim.x * blockDim.x) {
+		uint32_t sig = ld_stream_u32(in + 3 * i), hash = ld_stream_u32(in + 3 * i + 1),
+		         loc = ld_stream_u32(in + 3 * i + 2);
+		int z = delete_one<kPairs>(table, g, sig, hash, loc);
+		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+	}
+}
+
 // The legacy entry point only knows num_blks on the host; segment sizes live in device
 // memory (mega_scheduler.c:493-494).  So the grid is count-independent: every CTA builds
 // the prefix sum of the segment sizes in shared memory and the grid strides over the
 // concatenation.  Segment membership carries no meaning.
 constexpr int kMaxSegChunk = 1024;
 
+template <bool kPairs>
 __global__ void __launch_bounds__(256)
 insert_segments_kernel(Bucket* table, const uint32_t* const* __restrict__ blk_input,
 		const int* __restrict__ blk_elem_num, int num_blks, Geom g, Stats* st)
@@ -387,57 +513,75 @@ insert_segments_kernel(Bucket* table, const uint32_t* const* __restrict__ blk_in
 				e < total; e += (unsigned long long)gridDim.x * blockDim.x) {
 			while (e >= prefix[k + 1]) k++;                          // e only grows
 			const uint32_t* p = base[k] + 3 * (e - prefix[k]);
-			insert_one(table, g, ld_stream_u32(p), ld_stream_u32(p + 1), ld_stream_u32(p + 2), st);
+			insert_one<kPairs>(table, g, ld_stream_u32(p), ld_stream_u32(p + 1), ld_stream_u32(p + 2), st);
 		}
 	}
 }
 
 // host-known count (extended API, pipeline)
+template <bool kPairs>
 __global__ void __launch_bounds__(256)
 insert_flat_kernel(Bucket* table, const uint32_t* __restrict__ in, size_t n, Geom g, Stats* st)
 {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
 			i += (size_t)gridDim.x * blockDim.x)
-		insert_one(table, g, ld_stream_u32(in + 3 * i), ld_stream_u32(in + 3 * i + 1),
+		insert_one<kPairs>(table, g, ld_stream_u32(in + 3 * i), ld_stream_u32(in + 3 * i + 1),
 				ld_stream_u32(in + 3 * i + 2), st);
 }
 
 // Sequential execution of the SAME device code by one thread, segments in order, requests in
 // order: reproduces the oracle slot for slot at any load factor.  Used by the parity tests
 // (GPUHASH_INSERT_SERIAL); not a fast path.
+template <bool kPairs>
 __global__ void insert_serial_kernel(Bucket* table, const uint32_t* const* blk_input,
 		const int* blk_elem_num, int num_blks, const uint32_t* flat, size_t flat_n, Geom g, Stats* st)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (flat) {
 		for (size_t i = 0; i < flat_n; i++)
-			insert_one(table, g, flat[3 * i], flat[3 * i + 1], flat[3 * i + 2], st);
+			insert_one<kPairs>(table, g, flat[3 * i], flat[3 * i + 1], flat[3 * i + 2], st);
 		return;
 	}
 	for (int k = 0; k < num_blks; k++) {
 		const uint32_t* p = blk_input[k];
 		for (int i = 0; i < blk_elem_num[k]; i++)
-			insert_one(table, g, p[3 * i], p[3 * i + 1], p[3 * i + 2], st);
+			insert_one<kPairs>(table, g, p[3 * i], p[3 * i + 1], p[3 * i + 2], st);
 	}
 }
 
+template <bool kPairs>
 __global__ void delete_serial_kernel(const uint32_t* in, Bucket* table, size_t n, Geom g, Stats* st)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	for (size_t i = 0; i < n; i++) {
-		int z = delete_one(table, g, in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+		int z = delete_one<kPairs>(table, g, in[3 * i], in[3 * i + 1], in[3 * i + 2]);
 		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
 	}
 }
 
-#endif  /* GH_DEFINE_KERNELS */
+// In-place conversion between the two layouts (one thread per bucket):
+//   to_pairs: words (l, 8+l) -> (2l, 2l+1);  !to_pairs: the inverse.
+__global__ void __launch_bounds__(256)
+convert_layout_kernel(Bucket* table, size_t buckets, int to_pairs)
+{
+	for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < buckets;
+			b += (size_t)gridDim.x * blockDim.x) {
+		Bkt k = ld_bucket_strong(table + b);
+		uint32_t in[16], out[16];
+#pragma unroll
+		for (int i = 0; i < 8; i++) { in[i] = k.a.w[i]; in[8 + i] = k.b.w[i]; }
+#pragma unroll
+		for (int l = 0; l < 8; l++) {
+			if (to_pairs) { out[2 * l] = in[l]; out[2 * l + 1] = in[8 + l]; }
+			else          { out[l] = in[2 * l]; out[8 + l] = in[2 * l + 1]; }
+		}
+		uint4* dst = (uint4*)table[b].w;
+#pragma unroll
+		for (int i = 0; i < 4; i++) dst[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+	}
+}
 
-}  // namespace gh
-
-#ifdef GH_DEFINE_KERNELS
-/* ------------------------------------------------------------------ alternative search shape */
-
-namespace gh {
+/* ---- alternative search shape, kept for comparison (tools/sweep.py) ---- */
 
 __device__ __forceinline__ uint4 ld_half_row(const uint32_t* p)
 {
@@ -447,10 +591,9 @@ __device__ __forceinline__ uint4 ld_half_row(const uint32_t* p)
 	return v;
 }
 
-// Cooperative variant kept for comparison (tools/sweep.py, DESIGN.md "why one thread per request"):
-// four lanes per request -- lanes 0,1 take the two 16 B halves of bucket 1's signature row, lanes
-// 2,3 those of bucket 2 -- 128-bit loads, ballot inside the 4-lane group, the hit lane fetches the
-// location, lane 0 stores the pair.  Same results as search_kernel.
+// Split layout only: four lanes per request -- lanes 0,1 take the two 16 B halves of bucket 1's
+// signature row, lanes 2,3 those of bucket 2 -- 128-bit loads, ballot inside the 4-lane group,
+// the hit lane fetches the location, lane 0 stores the pair.  Same results as search_kernel.
 __global__ void __launch_bounds__(256)
 search_coop4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		const Bucket* __restrict__ table, size_t n, Geom g)
@@ -465,9 +608,9 @@ search_coop4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
 		uint32_t m = 0, loc = 0;
 		if (live) {
-			uint4 v = ld_half_row(table[b].sig + 4 * (sub & 1u));
+			uint4 v = ld_half_row(table[b].w + 4 * (sub & 1u));
 			m = (v.x == q.x ? 1u : 0u) | (v.y == q.x ? 2u : 0u) | (v.z == q.x ? 4u : 0u) | (v.w == q.x ? 8u : 0u);
-			if (m) loc = ld_u32_ro(&table[b].loc[4 * (sub & 1u) + (__ffs(m) - 1)]);
+			if (m) loc = ld_u32_ro(&table[b].w[8 + 4 * (sub & 1u) + (__ffs(m) - 1)]);
 		}
 		const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
 		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));   // lower half wins
@@ -476,6 +619,6 @@ search_coop4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 			st_stream_u2(out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
 	}
 }
+#endif  /* GH_DEFINE_KERNELS */
 
 }  // namespace gh
-#endif  /* GH_DEFINE_KERNELS */

@@ -129,9 +129,7 @@ search_segments_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, 
 		while (e >= prefix[s + 1]) s++;
 		const uint32_t j = e - prefix[s];
 		const uint2 q = ld_u2_sys((const uint2 *)seg_in.p[s] + j);
-		uint32_t b1, b2; gh::Row r1, r2;
-		gh::search_issue<false>(table, g, q, b1, b2, r1, r2);
-		const uint2 o = gh::search_finish(table, q, b1, b2, r1, r2);
+		const uint2 o = gh::search_one(table, g, q);
 		((uint2 *)seg_out.p[s])[j] = o;                               /* local staging or the origin's, over NVLink */
 	}
 }
@@ -186,9 +184,16 @@ delete_segments_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const 
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
 		while (e >= prefix[s + 1]) s++;
 		const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)(e - prefix[s]);
-		int z = gh::delete_one(table, g, p[0], p[1], p[2]);
+		int z = g.layout == gh::kLayoutPairs ? gh::delete_one<true>(table, g, p[0], p[1], p[2])
+		                                     : gh::delete_one<false>(table, g, p[0], p[1], p[2]);
 		if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
 	}
+}
+
+/* stream-ordered wait: everything enqueued after this kernel sees what the peers published before raising their flags */
+__global__ void wait_flags_kernel(const uint32_t *flags, int G, uint32_t want, uint32_t *err)
+{
+	if (threadIdx.x < G) wait_flag(flags + threadIdx.x, want, 2000000000ULL, err);
 }
 
 int fill_ptrs(Ptrs &P, const void *const *src, int G)
@@ -249,7 +254,7 @@ extern "C" int gpuhash_search_segments(const gpuhash_geom_t *g, const void *tabl
 	Ptrs I, O;
 	if (!g || fill_ptrs(I, seg_in_ptrs, num_seg) || fill_ptrs(O, seg_out_ptrs, num_seg) || !seg_count_d) return -1;
 	if (wait_seq && (!flags_d || !err_d)) return -1;
-	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo;
+	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo; gg.layout = g->layout;
 	search_segments_kernel<<<grid_for(max_total, 8), 256, 0, (cudaStream_t)stream>>>((const gh::Bucket *)table_d, gg, num_seg, I,
 			seg_count_d, O, flags_d, wait_seq, err_d);
 	return (int)cudaGetLastError();
@@ -281,9 +286,16 @@ extern "C" int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, i
 {
 	Ptrs I;
 	if (!g || fill_ptrs(I, seg_in_ptrs, num_seg) || !seg_count_d) return -1;
-	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo;
+	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo; gg.layout = g->layout;
 	delete_segments_kernel<<<grid_for(max_total, 8), 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, num_seg, I,
 			seg_count_d, (gh::Stats *)stats_d);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t want, uint32_t *err_d, void *stream)
+{
+	if (!flags_d || !err_d || num < 1 || num > kMaxShards) return -1;
+	wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_d, num, want, err_d);
 	return (int)cudaGetLastError();
 }
 

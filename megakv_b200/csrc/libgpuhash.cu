@@ -31,12 +31,18 @@ static_assert(sizeof(gpuhash_stats_t) == sizeof(gh::Stats), "stats mirror");
 #endif
 
 /* process-wide defaults of the legacy entry points = the header this file was compiled with */
+#if defined(GPUHASH_DEFAULT_LAYOUT_REFERENCE)
+#  define GH_DEFAULT_LAYOUT GPUHASH_LAYOUT_REFERENCE
+#else
+#  define GH_DEFAULT_LAYOUT GPUHASH_LAYOUT_PAIRS
+#endif
 static gpuhash_geom_t g_default_geom = {
-	(uint32_t)HASH_MASK, (uint32_t)BLOCK_HASH_MASK, GH_DEFAULT_ALGO, 5u
+	(uint32_t)HASH_MASK, (uint32_t)BLOCK_HASH_MASK, GH_DEFAULT_ALGO, 5u, GH_DEFAULT_LAYOUT
 };
 static gpuhash_tune_t g_tune = { 0, 0, 4 };
 
 static int g_sm_count[64];          /* 0 = not queried yet */
+static int g_l2_bytes[64];
 
 static int sm_count_now(void)
 {
@@ -50,9 +56,22 @@ static int sm_count_now(void)
 	return g_sm_count[dev];
 }
 
+static size_t l2_bytes_now(void)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (size_t)126 << 20;
+	if (g_l2_bytes[dev] == 0) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev) != cudaSuccess || n <= 0) n = 126 << 20;
+		g_l2_bytes[dev] = n;
+	}
+	return (size_t)g_l2_bytes[dev];
+}
+
 static inline gh::Geom to_geom(const gpuhash_geom_t *g)
 {
 	gh::Geom r; r.hash_mask = g->hash_mask; r.block_mask = g->block_mask; r.algo = g->algo; r.max_cuckoo = g->max_cuckoo;
+	r.layout = g->layout;
 	return r;
 }
 
@@ -73,6 +92,7 @@ extern "C" int gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int l
 	g->block_mask = (uint32_t)((1ULL << (mem_p_total - 6 - 3)) - 1);
 	g->algo = algo;
 	g->max_cuckoo = 5;
+	g->layout = GPUHASH_LAYOUT_PAIRS;
 	return 0;
 }
 
@@ -88,62 +108,84 @@ extern "C" void gpuhash_get_tuning(gpuhash_tune_t *t) { *t = g_tune; }
 
 /* ------------------------------------------------------------------ launches */
 
-template <int kQpt>
-static void launch_search(const uint2 *in, uint2 *out, const gh::Bucket *table, size_t n,
+template <int kQpt, int kMode>
+static void launch_search_mode(const uint2 *in, uint2 *out, const gh::Bucket *table, size_t n,
 		const gh::Geom &g, gh::Stats *st, cudaStream_t s)
 {
 	size_t blocks = (n + (size_t)256 * kQpt - 1) / ((size_t)256 * kQpt);
 	if (blocks > 0x7fffffffULL) blocks = 0x7fffffffULL;
-	if (g_tune.search_prefetch_loc)
-		gh::search_kernel<kQpt, true><<<(unsigned)blocks, 256, 0, s>>>(in, out, table, n, g, st);
-	else
-		gh::search_kernel<kQpt, false><<<(unsigned)blocks, 256, 0, s>>>(in, out, table, n, g, st);
+	gh::search_kernel<kQpt, kMode><<<(unsigned)blocks, 256, 0, s>>>(in, out, table, n, g, st);
+}
+
+template <int kQpt>
+static void launch_search(int mode, const uint2 *in, uint2 *out, const gh::Bucket *table, size_t n,
+		const gh::Geom &g, gh::Stats *st, cudaStream_t s)
+{
+	if (mode == gh::kSearchPairs)           launch_search_mode<kQpt, gh::kSearchPairs>(in, out, table, n, g, st, s);
+	else if (mode == gh::kSearchSplitWhole) launch_search_mode<kQpt, gh::kSearchSplitWhole>(in, out, table, n, g, st, s);
+	else                                    launch_search_mode<kQpt, gh::kSearchSplitLazy>(in, out, table, n, g, st, s);
 }
 
 extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, void *out_d,
 		const void *table_d, size_t n, gpuhash_stats_t *stats_d, void *stream)
 {
-	if (!g || (n && (!selem_d || !out_d || !table_d))) return -1;
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || (n && (!selem_d || !out_d || !table_d))) return -1;
 	if (n == 0) return 0;
 	int qpt = g_tune.search_qpt;
 	if (qpt == 0) {
 		/* one request per thread until every SM has a full complement of warps, then add
 		 * independent loads per thread instead of more (queued) CTAs */
 		size_t full = (size_t)sm_count_now() * 2048;
-		qpt = n <= full ? 1 : (n <= 4 * full ? 2 : 4);
+		qpt = n <= full ? 1 : 2;
 	}
 	const uint2 *in = (const uint2 *)selem_d; uint2 *out = (uint2 *)out_d;
 	const gh::Bucket *t = (const gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
-	if (qpt < 0) {                                   /* comparison shape: 4 lanes per request */
-		size_t blocks = (n * 4 + 255) / 256;
-		size_t cap = (size_t)sm_count_now() * 64;
-		if (blocks > cap) blocks = cap;
-		gh::search_coop4_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg);
-		return (int)cudaGetLastError();
+	int mode = gh::kSearchPairs;
+	if (g->layout == GPUHASH_LAYOUT_REFERENCE) {
+		/* in HBM a probe costs a whole 128 B line whatever is asked of it, so take the location row with the
+		 * signature row; in L2 sectors are the cost, so fetch the location word only on a hit */
+		if (g_tune.search_split_mode == 1) mode = gh::kSearchSplitLazy;
+		else if (g_tune.search_split_mode == 2) mode = gh::kSearchSplitWhole;
+		else mode = gpuhash_table_bytes(g) > l2_bytes_now() ? gh::kSearchSplitWhole : gh::kSearchSplitLazy;
+		if (qpt < 0) {                               /* comparison shape: 4 lanes per request */
+			size_t blocks = (n * 4 + 255) / 256;
+			size_t cap = (size_t)sm_count_now() * 64;
+			if (blocks > cap) blocks = cap;
+			gh::search_coop4_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg);
+			return (int)cudaGetLastError();
+		}
 	}
-	if (qpt >= 4)      launch_search<4>(in, out, t, n, gg, st, s);
-	else if (qpt >= 2) launch_search<2>(in, out, t, n, gg, st, s);
-	else               launch_search<1>(in, out, t, n, gg, st, s);
+	if (qpt >= 4)      launch_search<4>(mode, in, out, t, n, gg, st, s);
+	else if (qpt >= 2) launch_search<2>(mode, in, out, t, n, gg, st, s);
+	else               launch_search<1>(mode, in, out, t, n, gg, st, s);
 	return (int)cudaGetLastError();
 }
 
 extern "C" int gpuhash_insert_ex(const gpuhash_geom_t *g, void *table_d, const void *const *blk_input_d,
 		const int *blk_elem_num_d, int num_blks, gpuhash_stats_t *stats_d, unsigned flags, void *stream)
 {
-	if (!g || num_blks < 0 || (num_blks && (!table_d || !blk_input_d || !blk_elem_num_d))) return -1;
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || num_blks < 0 || (num_blks && (!table_d || !blk_input_d || !blk_elem_num_d))) return -1;
 	if (num_blks == 0) return 0;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
 	if (flags & GPUHASH_INSERT_SERIAL) {
-		gh::insert_serial_kernel<<<1, 32, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *const *)blk_input_d,
-				blk_elem_num_d, num_blks, nullptr, 0, gg, (gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::insert_serial_kernel<true><<<1, 32, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *const *)blk_input_d,
+					blk_elem_num_d, num_blks, nullptr, 0, gg, (gh::Stats *)stats_d);
+		else
+			gh::insert_serial_kernel<false><<<1, 32, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *const *)blk_input_d,
+					blk_elem_num_d, num_blks, nullptr, 0, gg, (gh::Stats *)stats_d);
 	} else {
 		int per_sm = g_tune.insert_ctas_per_sm > 0 ? g_tune.insert_ctas_per_sm : 4;
 		unsigned blocks = (unsigned)(sm_count_now() * per_sm);
-		gh::insert_segments_kernel<<<blocks, 256, 0, s>>>((gh::Bucket *)table_d,
-				(const uint32_t *const *)blk_input_d, blk_elem_num_d, num_blks, gg, (gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::insert_segments_kernel<true><<<blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+					(const uint32_t *const *)blk_input_d, blk_elem_num_d, num_blks, gg, (gh::Stats *)stats_d);
+		else
+			gh::insert_segments_kernel<false><<<blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+					(const uint32_t *const *)blk_input_d, blk_elem_num_d, num_blks, gg, (gh::Stats *)stats_d);
 	}
 	return (int)cudaGetLastError();
 }
@@ -151,19 +193,27 @@ extern "C" int gpuhash_insert_ex(const gpuhash_geom_t *g, void *table_d, const v
 extern "C" int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *ielem_d, size_t n,
 		gpuhash_stats_t *stats_d, unsigned flags, void *stream)
 {
-	if (!g || (n && (!table_d || !ielem_d))) return -1;
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || (n && (!table_d || !ielem_d))) return -1;
 	if (n == 0) return 0;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
 	if (flags & GPUHASH_INSERT_SERIAL) {
-		gh::insert_serial_kernel<<<1, 32, 0, s>>>((gh::Bucket *)table_d, nullptr, nullptr, 0,
-				(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::insert_serial_kernel<true><<<1, 32, 0, s>>>((gh::Bucket *)table_d, nullptr, nullptr, 0,
+					(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+		else
+			gh::insert_serial_kernel<false><<<1, 32, 0, s>>>((gh::Bucket *)table_d, nullptr, nullptr, 0,
+					(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
 	} else {
 		size_t blocks = (n + 255) / 256;
 		size_t cap = (size_t)sm_count_now() * 32;        /* grid-stride beyond 32 CTAs per SM */
 		if (blocks > cap) blocks = cap;
-		gh::insert_flat_kernel<<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d,
-				(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::insert_flat_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+					(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+		else
+			gh::insert_flat_kernel<false><<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d,
+					(const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
 	}
 	return (int)cudaGetLastError();
 }
@@ -171,20 +221,37 @@ extern "C" int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, co
 extern "C" int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_d, size_t n,
 		gpuhash_stats_t *stats_d, unsigned flags, void *stream)
 {
-	if (!g || (n && (!table_d || !delem_d))) return -1;
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || (n && (!table_d || !delem_d))) return -1;
 	if (n == 0) return 0;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
 	if (flags & GPUHASH_INSERT_SERIAL) {
-		gh::delete_serial_kernel<<<1, 32, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg,
-				(gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::delete_serial_kernel<true><<<1, 32, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);
+		else
+			gh::delete_serial_kernel<false><<<1, 32, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);
 	} else {
 		size_t blocks = (n + 255) / 256;
 		size_t cap = (size_t)sm_count_now() * 32;
 		if (blocks > cap) blocks = cap;
-		gh::delete_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg,
-				(gh::Stats *)stats_d);
+		if (gg.layout == gh::kLayoutPairs)
+			gh::delete_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);
+		else
+			gh::delete_kernel<false><<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);
 	}
+	return (int)cudaGetLastError();
+}
+
+/* Rewrites the table in place from its current layout (g->layout) to `to_layout`.  The caller updates g->layout. */
+extern "C" int gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, unsigned to_layout, void *stream)
+{
+	if (!g || !table_d || g->layout > GPUHASH_LAYOUT_REFERENCE || to_layout > GPUHASH_LAYOUT_REFERENCE) return -1;
+	if (g->layout == to_layout) return 0;
+	size_t buckets = (size_t)g->hash_mask + 1;
+	size_t blocks = (buckets + 255) / 256, cap = (size_t)sm_count_now() * 32;
+	if (blocks > cap) blocks = cap;
+	gh::convert_layout_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, buckets,
+			to_layout == GPUHASH_LAYOUT_PAIRS);
 	return (int)cudaGetLastError();
 }
 

@@ -27,9 +27,10 @@ def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def make_geom(mem_p, algo=N.CUCKOO, log2_shards=0):
+def make_geom(mem_p, algo=N.CUCKOO, log2_shards=0, layout=N.LAYOUT_PAIRS):
     g = N.Geom()
     N.check(N.lib().gpuhash_geom_init_shard(C.byref(g), mem_p, log2_shards, algo), "gpuhash_geom_init")
+    g.layout = layout
     return g
 
 
@@ -84,11 +85,34 @@ class DeviceBuffer:
 
 
 class DeviceTable(DeviceBuffer):
-    """One cudaMalloc(HT_SIZE) + cudaMemset(0), as mega_scheduler.c:273-274 / insert_test.c:80-81."""
+    """One cudaMalloc(HT_SIZE) + cudaMemset(0), as mega_scheduler.c:273-274 / insert_test.c:80-81.
+    `layout` is how the library lays slots out inside the 64 B buckets (gpuhash_ex.h); host images are
+    always exchanged in the reference's bucket_t layout."""
 
-    def __init__(self, mem_p, algo=N.CUCKOO):
-        self.geom = make_geom(mem_p, algo)
+    def __init__(self, mem_p, algo=N.CUCKOO, layout=N.LAYOUT_PAIRS, log2_shards=0):
+        self.geom = make_geom(mem_p, algo, log2_shards, layout)
         super().__init__(N.lib().gpuhash_table_bytes(C.byref(self.geom)), zero=True)
+
+    def load_reference(self, words):
+        """upload a table image in the reference byte layout (bucket_t[], gpu_hash.h:79-82)"""
+        self.upload(np.ascontiguousarray(words).view(np.uint32))
+        if self.geom.layout != N.LAYOUT_REFERENCE:
+            as_ref = N.Geom.from_buffer_copy(bytes(self.geom)); as_ref.layout = N.LAYOUT_REFERENCE
+            N.check(N.lib().gpuhash_table_convert(C.byref(as_ref), self.ptr, self.geom.layout, None))
+            N.check(N.lib().gpuhash_device_sync())
+
+    def dump_reference(self):
+        """the table as the reference would hold it (converted on the device, table left unchanged)"""
+        L = N.lib()
+        N.check(L.gpuhash_device_sync())
+        if self.geom.layout == N.LAYOUT_REFERENCE:
+            return self.download(np.uint32)
+        N.check(L.gpuhash_table_convert(C.byref(self.geom), self.ptr, N.LAYOUT_REFERENCE, None))
+        out = self.download(np.uint32)
+        as_ref = N.Geom.from_buffer_copy(bytes(self.geom)); as_ref.layout = N.LAYOUT_REFERENCE
+        N.check(L.gpuhash_table_convert(C.byref(as_ref), self.ptr, self.geom.layout, None))
+        N.check(L.gpuhash_device_sync())
+        return out
 
     def make_default(self):
         """Make this geometry the one the three legacy entry points use."""
@@ -141,11 +165,12 @@ def split_insert_blocks(iel, num_blks=INSERT_BLOCK):
 class GpuHashIndex:
     """Table + per-worker streams and staging; ``cycle`` is one pass of mega_scheduler.c:392-504."""
 
-    def __init__(self, mem_p, algo=N.CUCKOO, workers=1, max_search=1 << 16, max_insert=1 << 16, max_delete=1 << 16):
+    def __init__(self, mem_p, algo=N.CUCKOO, workers=1, max_search=1 << 16, max_insert=1 << 16, max_delete=1 << 16,
+                 layout=N.LAYOUT_PAIRS):
         N.require_gpu()
         self.L = N.lib()
         self.mem_p, self.algo, self.workers = mem_p, algo, workers
-        self.h = self.L.gpuhash_index_create(mem_p, algo, workers, max_search, max_insert, max_delete)
+        self.h = self.L.gpuhash_index_create_layout(mem_p, algo, layout, workers, max_search, max_insert, max_delete)
         if not self.h:
             raise N.GpuHashError("gpuhash_index_create failed (out of device memory?)")
         self.geom = self.L.gpuhash_index_geom(self.h).contents

@@ -68,24 +68,25 @@ def test_oracle_reproduces_reference_kernels(path):
 # ------------------------------------------------------------------ GPU: CUDA path vs reference
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 1], ids=["pairs", "reflayout"])
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
-def test_cuda_path_reproduces_reference_kernels(gpu, path):
+def test_cuda_path_reproduces_reference_kernels(gpu, path, layout):
     import megakv_b200 as mk
     from tests.test_gpu_parity import gpu_search, gpu_insert, gpu_delete
     g, kind, algo, mem_p = load(path)
-    t = mk.DeviceTable(mem_p, algo)
+    t = mk.DeviceTable(mem_p, algo, layout)
     if kind == "search":
-        t.upload(g["table"])
+        t.load_reference(g["table"])
         assert np.array_equal(gpu_search(t, g["sel"].view(mk.SEL_DT), prezero=False), g["out"])
-        t.upload(g["dup_table"])
+        t.load_reference(g["dup_table"])
         assert np.array_equal(gpu_search(t, g["dup_sel"].view(mk.SEL_DT)), g["dup_out"])
     elif kind == "delete":
-        t.upload(g["table_in"])
+        t.load_reference(g["table_in"])
         gpu_delete(t, g["dele"].view(mk.IEL_DT))
-        assert np.array_equal(t.download(np.uint32), g["table"])
+        assert np.array_equal(t.dump_reference(), g["table"])
     elif kind == "serial":
         gpu_insert(t, g["iel"].view(mk.IEL_DT), flags=mk.INSERT_SERIAL)
-        assert np.array_equal(t.download(np.uint32), g["table"])
+        assert np.array_equal(t.dump_reference(), g["table"])
         assert np.array_equal(gpu_search(t, g["sel"].view(mk.SEL_DT), prezero=False), g["out"])
     elif kind == "batch":
         o = po.Oracle(mem_p, algo)
@@ -97,4 +98,4 @@ def test_cuda_path_reproduces_reference_kernels(gpu, path):
             assert np.array_equal(np.sort(gpu_search(t, sel).reshape(-1, 2), 1), np.sort(g["outs"][it].reshape(-1, 2), 1))
             if it % 2:
                 gpu_delete(t, iel[: n // 2])
-            assert o.digest(table=t.download(np.uint32)) == o.digest(table=g["tables"][it])
+            assert o.digest(table=t.dump_reference()) == o.digest(table=g["tables"][it])

@@ -66,8 +66,9 @@ def gather_sweep(table, nbytes, tag):
                  Gunits_per_s=round(units / 1e9, 3), GBps_useful=round(units * (64 if mode == 2 else 32) / 1e9, 1))
 
 
-def search_sweep(mem_p, tag):
-    t = mk.DeviceTable(mem_p)
+def search_sweep(mem_p, tag, layout=N.LAYOUT_PAIRS):
+    t = mk.DeviceTable(mem_p, layout=layout)
+    tag = tag + ("/pairs" if layout == N.LAYOUT_PAIRS else "/reflayout")
     geom = t.geom
     pop = (1 << mem_p) // 8 // 4
     dt = preload(geom, t.ptr, pop)
@@ -79,8 +80,8 @@ def search_sweep(mem_p, tag):
     old = N.Tune(); L.gpuhash_get_tuning(C.byref(old))
     # ---- 2: kernel shape, one launch at a time
     for n in (1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24):
-        for qpt in (1, 2, 4, -1):
-            for pf in ((0, 1) if qpt > 0 else (0,)):
+        for qpt in (1, 2, 4):
+            for pf in (0,):
                 L.gpuhash_set_tuning(C.byref(N.Tune(qpt, pf, 4)))
                 reps = max(3, min(200, (1 << 24) // n))
                 ms = timed_resident(geom, t.ptr, sd.ptr, n, od.ptr, None, 0, reps, 1, 0) / reps
@@ -96,7 +97,7 @@ def search_sweep(mem_p, tag):
             emit(exp="search_64k_pipeline", table=tag, streams=streams, graph=graph, us_per_batch=round(ms / steps * 1e3, 3),
                  Mops=round(n * steps / ms / 1e3, 1), GBps_112=round(n * steps * 112 / ms / 1e6, 1))
     for qpt in (1, 2):
-        for pf in (0, 1):
+        for pf in (0,):
             L.gpuhash_set_tuning(C.byref(N.Tune(qpt, pf, 4)))
             ms = timed_resident(geom, t.ptr, sd.ptr, n, od.ptr, None, 0, steps, 8, 1)
             emit(exp="search_64k_shape", table=tag, qpt=qpt, prefetch=pf, streams=8, graph=1,
@@ -151,17 +152,22 @@ def fill_sweep(mem_p, algo, tag):
 
 def main():
     mk.require_gpu()
+    only = set(sys.argv[1:]) or {"gather", "search", "fill"}
     sm, l2 = C.c_int(), C.c_int(); free, total = C.c_size_t(), C.c_size_t()
     N.check(L.gpuhash_device_info(0, C.byref(sm), C.byref(l2), C.byref(free), C.byref(total)))
     emit(exp="device", sm_count=sm.value, l2_bytes=l2.value, free_gib=round(free.value / 2**30, 1), build=L.gpuhash_build_info().decode())
-    big = mk.DeviceBuffer(1 << 34, zero=True)
-    gather_sweep(big.ptr, 1 << 34, "16GiB")
-    gather_sweep(big.ptr, 1 << 26, "64MiB(L2)")
-    big.free()
-    search_sweep(34, "MEM_P34")
-    search_sweep(26, "MEM_P26")
-    fill_sweep(26, N.CUCKOO, "MEM_P26")
-    fill_sweep(26, N.TWO_CHOICE, "MEM_P26")
+    if "gather" in only:
+        big = mk.DeviceBuffer(1 << 34, zero=True)
+        gather_sweep(big.ptr, 1 << 34, "16GiB")
+        gather_sweep(big.ptr, 1 << 26, "64MiB(L2)")
+        big.free()
+    if "search" in only:
+        for layout in (N.LAYOUT_PAIRS, N.LAYOUT_REFERENCE):
+            search_sweep(34, "MEM_P34", layout)
+            search_sweep(26, "MEM_P26", layout)
+    if "fill" in only:
+        fill_sweep(26, N.CUCKOO, "MEM_P26")
+        fill_sweep(26, N.TWO_CHOICE, "MEM_P26")
     emit(exp="done")
 
 
