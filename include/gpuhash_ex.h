@@ -68,8 +68,9 @@ void   gpuhash_get_default_geom(gpuhash_geom_t *g);
 
 /* ---- launch tuning (process-wide; defaults are what bench.py measures) ---- */
 typedef struct gpuhash_tune_s {
-	int search_qpt;          /* requests per thread: 1, 2 or 4; 0 = choose from batch size;
-	                            -1 = the 4-lanes-per-request comparison kernel */
+	int search_qpt;          /* 0 = choose (default); -4 = four lanes per request, one L2 request per bucket;
+	                            1, 2, 4 = one thread per request, that many requests per thread;
+	                            -1 = 4 lanes x 128-bit loads (reference layout only; comparison kernel) */
 	int search_split_mode;   /* REFERENCE layout only: 0 = by table size, 1 = location word on hit only, 2 = whole buckets */
 	int insert_ctas_per_sm;  /* grid of the count-independent insert kernel */
 } gpuhash_tune_t;

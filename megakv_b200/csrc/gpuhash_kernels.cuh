@@ -581,6 +581,68 @@ convert_layout_kernel(Bucket* table, size_t buckets, int to_pairs)
 	}
 }
 
+/* ---- four lanes per request: every bucket is ONE L2 request ---- */
+
+// Lane j of a 4-lane group loads sector j of the request's four sectors {b1.lo, b1.hi, b2.lo, b2.hi} in the SAME
+// load instruction, so the two sectors of a bucket leave the SM as one request for one 128 B line.  Measured on
+// B200 (tools/gather_flavours, profiles/): what is scarce beyond L2 is requests to lines that are not resident
+// (~47 G/s), not bytes; two sectors asked for by two instructions cost two requests, asked for by two lanes of one
+// instruction they cost one.  Results identical to search_kernel.
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+search_quad_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
+		const Bucket* __restrict__ table, size_t n, Geom g, Stats* st)
+{
+	const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
+	const size_t per_iter = ((size_t)gridDim.x * blockDim.x) >> 2;
+	const size_t n_up = (n + 7) & ~(size_t)7;                        // warp-uniform trip count
+	for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < n_up; i += per_iter) {
+		const bool live = i < n;
+		uint2 q = make_uint2(0u, 0u);
+		Row r;
+#pragma unroll
+		for (int k = 0; k < 8; k++) r.w[k] = 0;
+		if (live) {
+			q = ld_stream_u2(in + i);
+			const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
+			r = ld_row_ro(table[b].w + 8 * half);
+		}
+		uint32_t m, loc = 0;
+		if (kPairs) {                                                // this lane holds slots 4*half .. 4*half+3 as {sig, loc}
+			m = (r.w[0] == q.x ? 1u : 0u) | (r.w[2] == q.x ? 2u : 0u) | (r.w[4] == q.x ? 4u : 0u) | (r.w[6] == q.x ? 8u : 0u);
+			loc = (m & 1u) ? r.w[1] : (m & 2u) ? r.w[3] : (m & 4u) ? r.w[5] : r.w[7];
+			if (!live) m = 0;
+			const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+			const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));   // lowest slot wins
+			const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
+			if (live && sub == 0) {
+				st_stream_u2(out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
+				if (st) { if (hits & 3u) atomicAdd(&st->search_hits_b1, 1ULL); if (hits & 12u) atomicAdd(&st->search_hits_b2, 1ULL); }
+			}
+		} else {                                                     // even lanes hold a signature row, odd lanes its location row
+			m = live ? eq_mask(r, q.x) : 0u;
+			const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));            // mask of this bucket's signature lane
+			const int l = __ffs(msig | 0x100u) - 1 & 7;
+			loc = r.w[0];
+			if (l == 1) loc = r.w[1];
+			if (l == 2) loc = r.w[2];
+			if (l == 3) loc = r.w[3];
+			if (l == 4) loc = r.w[4];
+			if (l == 5) loc = r.w[5];
+			if (l == 6) loc = r.w[6];
+			if (l == 7) loc = r.w[7];
+			if (!msig) loc = 0;
+			const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + 1);
+			const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + 3);
+			const uint32_t m2 = __shfl_sync(0xffffffffu, m, grp0 + 2);
+			if (live && sub == 0) {
+				st_stream_u2(out + i, make_uint2(l0, l1));
+				if (st) { if (m) atomicAdd(&st->search_hits_b1, 1ULL); if (m2) atomicAdd(&st->search_hits_b2, 1ULL); }
+			}
+		}
+	}
+}
+
 /* ---- alternative search shape, kept for comparison (tools/sweep.py) ---- */
 
 __device__ __forceinline__ uint4 ld_half_row(const uint32_t* p)

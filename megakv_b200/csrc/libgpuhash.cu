@@ -133,23 +133,34 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 	if (n == 0) return 0;
 	int qpt = g_tune.search_qpt;
 	if (qpt == 0) {
-		/* one request per thread until every SM has a full complement of warps, then add
-		 * independent loads per thread instead of more (queued) CTAs */
-		size_t full = (size_t)sm_count_now() * 2048;
-		qpt = n <= full ? 1 : 2;
+		/* Beyond L2 the scarce resource is L2 requests for non-resident 128 B lines (~47 G/s on B200), and the
+		 * two sectors of a bucket cost ONE request only when two lanes ask for them in the same instruction
+		 * (profiles/r01_l2_requests.md): four lanes per request.  The pair layout needs whole buckets anyway,
+		 * so it always takes that shape.  The reference layout on an L2-resident table is cheapest with one
+		 * thread per request reading the signature rows and, on a hit only, the location word. */
+		if (g->layout == GPUHASH_LAYOUT_PAIRS || gpuhash_table_bytes(g) > l2_bytes_now()) qpt = -4;
+		else qpt = n <= (size_t)sm_count_now() * 2048 ? 1 : 2;
 	}
 	const uint2 *in = (const uint2 *)selem_d; uint2 *out = (uint2 *)out_d;
 	const gh::Bucket *t = (const gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
+	if (qpt == -4) {                                 /* four lanes per request, one L2 request per bucket */
+		size_t blocks = (n * 4 + 255) / 256;
+		size_t cap = (size_t)sm_count_now() * 64;
+		if (blocks > cap) blocks = cap;
+		if (g->layout == GPUHASH_LAYOUT_PAIRS) gh::search_quad_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st);
+		else                                   gh::search_quad_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st);
+		return (int)cudaGetLastError();
+	}
 	int mode = gh::kSearchPairs;
 	if (g->layout == GPUHASH_LAYOUT_REFERENCE) {
 		/* in HBM a probe costs a whole 128 B line whatever is asked of it, so take the location row with the
 		 * signature row; in L2 sectors are the cost, so fetch the location word only on a hit */
 		if (g_tune.search_split_mode == 1) mode = gh::kSearchSplitLazy;
 		else if (g_tune.search_split_mode == 2) mode = gh::kSearchSplitWhole;
-		else mode = gpuhash_table_bytes(g) > l2_bytes_now() ? gh::kSearchSplitWhole : gh::kSearchSplitLazy;
-		if (qpt < 0) {                               /* comparison shape: 4 lanes per request */
+		else mode = gh::kSearchSplitLazy;
+		if (qpt == -1) {                             /* comparison shape: 4 lanes per request, 128-bit loads */
 			size_t blocks = (n * 4 + 255) / 256;
 			size_t cap = (size_t)sm_count_now() * 64;
 			if (blocks > cap) blocks = cap;

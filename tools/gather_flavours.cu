@@ -50,13 +50,15 @@ LD1(ld1_ca, "ld.global.ca.u32")
 LD1(ld1_cg, "ld.global.cg.u32")
 
 enum { F_CA8, F_NA8, F_CG8, F_NC8, F_CV8, F_EF8, F_EL8, F_CS8, F_LU8, F_CA4x2, F_NA4x2, F_CG4x2, F_CA4, F_CG4, F_CA1, F_CG1,
-       F_ATOM, F_CPASYNC16, F_BULK32, F_COOP8, F_COUNT };
+       F_ATOM, F_CPASYNC16, F_BULK32, F_COOP8, F_PAIR2_1I, F_PAIR2_2I, F_QUAD4_1I, F_COUNT };
 static const char *kNames[F_COUNT] = {
 	"ld.ca.v8 (32B)", "ld.L1::no_allocate.v8 (32B)", "ld.cg.v8 (32B)", "ld.nc.v8 (32B)", "ld.volatile.v8 (32B)",
 	"ld.na.L2::evict_first.v8", "ld.na.L2::evict_last.v8", "ld.cs.v8 (32B)", "ld.lu.v8 (32B)",
 	"2 x ld.ca.v4 (32B)", "2 x ld.na.v4 (32B)", "2 x ld.cg.v4 (32B)", "ld.ca.v4 (16B only)", "ld.cg.v4 (16B only)",
 	"ld.ca.u32 (4B only)", "ld.cg.u32 (4B only)", "atom.add.u32 +0 (4B)", "cp.async.cg 2x16B -> smem", "cp.async.bulk 32B -> smem",
-	"8 lanes x ld.ca.u32 (32B coop)" };
+	"8 lanes x ld.ca.u32 (32B coop)",
+	"64B bucket: 2 lanes, ONE ld.v8 instruction (n counts buckets)", "64B bucket: 1 thread, TWO ld.v8 instructions (n counts buckets)",
+	"128B line: 4 lanes, ONE ld.v8 instruction (n counts lines)" };
 
 template <int F, int ILP>
 __global__ void __launch_bounds__(256)
@@ -80,6 +82,8 @@ gather(uint32_t *table, uint64_t mask, size_t n, uint32_t seed, uint32_t *sink)
 		for (int k = 0; k < ILP; k++) {
 			size_t idx = i + k;
 			if (F == F_COOP8) idx = (i / ILP / 8) * ILP + k + (size_t)seed;     // 8 neighbouring lanes share one sector
+			if (F == F_PAIR2_1I) idx = (i / ILP / 2) * ILP + k;                 // 2 neighbouring lanes share one bucket
+			if (F == F_QUAD4_1I) idx = (i / ILP / 4) * ILP + k;                 // 4 neighbouring lanes share one line
 			uint64_t u = mix64((uint64_t)idx * 0x9E3779B97F4A7C15ULL + seed) & mask;
 			uint32_t *p = table + u * 8;
 			if (F == F_CA8) v[k] = ld8_ca(p);
@@ -100,6 +104,9 @@ gather(uint32_t *table, uint64_t mask, size_t n, uint32_t seed, uint32_t *sink)
 			else if (F == F_CG1) v[k] = ld1_cg(p);
 			else if (F == F_ATOM) v[k] = atomicAdd(p, 0u);
 			else if (F == F_COOP8) v[k] = ld1_ca(p + (threadIdx.x & 7));
+			else if (F == F_PAIR2_1I) v[k] = ld8_na(table + (u & ~1ULL) * 8 + (threadIdx.x & 1) * 8);
+			else if (F == F_PAIR2_2I) { uint32_t *b = table + (u & ~1ULL) * 8; v[k] = ld8_na(b) ^ ld8_na(b + 8); }
+			else if (F == F_QUAD4_1I) v[k] = ld8_na(table + (u & ~3ULL) * 8 + (threadIdx.x & 3) * 8);
 			else if (F == F_CPASYNC16) {
 				uint32_t s = (uint32_t)__cvta_generic_to_shared(&stage[threadIdx.x * 8]);
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(p) : "memory");
@@ -171,6 +178,6 @@ int main(int argc, char **argv)
 #define RUN(F) ms = run<F>(table, mask, n, 77, sink); \
 	printf("{\"flavour\": \"%s\", \"ms\": %.4f, \"Gaccess_per_s\": %.2f}\n", kNames[F], ms, n / (ms * 1e-3) / 1e9); fflush(stdout);
 	RUN(F_CA8) RUN(F_NA8) RUN(F_CG8) RUN(F_NC8) RUN(F_CV8) RUN(F_EF8) RUN(F_EL8) RUN(F_CS8) RUN(F_LU8)
-	RUN(F_CA4x2) RUN(F_NA4x2) RUN(F_CG4x2) RUN(F_CA4) RUN(F_CG4) RUN(F_CA1) RUN(F_CG1) RUN(F_ATOM) RUN(F_CPASYNC16) RUN(F_COOP8) RUN(F_BULK32)
+	RUN(F_CA4x2) RUN(F_NA4x2) RUN(F_CG4x2) RUN(F_CA4) RUN(F_CG4) RUN(F_CA1) RUN(F_CG1) RUN(F_ATOM) RUN(F_CPASYNC16) RUN(F_COOP8) RUN(F_PAIR2_1I) RUN(F_PAIR2_2I) RUN(F_QUAD4_1I) RUN(F_BULK32)
 	return 0;
 }

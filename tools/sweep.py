@@ -80,10 +80,10 @@ def search_sweep(mem_p, tag, layout=N.LAYOUT_PAIRS):
     old = N.Tune(); L.gpuhash_get_tuning(C.byref(old))
     # ---- 2: kernel shape, one launch at a time
     for n in (1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24):
-        for qpt in (1, 2, 4):
+        for qpt in (1, 2, 4, -4):
             for pf in (0,):
                 L.gpuhash_set_tuning(C.byref(N.Tune(qpt, pf, 4)))
-                reps = max(3, min(200, (1 << 24) // n))
+                reps = max(1, min(200, nmax // n))                 # reps * n requests must stay inside the buffers
                 ms = timed_resident(geom, t.ptr, sd.ptr, n, od.ptr, None, 0, reps, 1, 0) / reps
                 emit(exp="search_shape", table=tag, n=n, qpt=qpt, prefetch=pf, us_per_launch=round(ms * 1e3, 3),
                      Mops=round(n / ms / 1e3, 1), GBps_112=round(n * 112 / ms / 1e6, 1))
@@ -96,7 +96,7 @@ def search_sweep(mem_p, tag, layout=N.LAYOUT_PAIRS):
             ms = timed_resident(geom, t.ptr, sd.ptr, n, od.ptr, None, 0, steps, streams, graph)
             emit(exp="search_64k_pipeline", table=tag, streams=streams, graph=graph, us_per_batch=round(ms / steps * 1e3, 3),
                  Mops=round(n * steps / ms / 1e3, 1), GBps_112=round(n * steps * 112 / ms / 1e6, 1))
-    for qpt in (1, 2):
+    for qpt in (1, 2, -4):
         for pf in (0,):
             L.gpuhash_set_tuning(C.byref(N.Tune(qpt, pf, 4)))
             ms = timed_resident(geom, t.ptr, sd.ptr, n, od.ptr, None, 0, steps, 8, 1)
