@@ -1,0 +1,278 @@
+"""Sharded hash index: one process per GPU, the logical table cut into G = world_size bucket ranges.
+
+The reference is single-GPU (src/mega.c:410).  Sharding is exact because both candidate buckets of a key and
+every bucket its eviction chain can reach share the top IBLOCK_P = 3 bits of the bucket index (gpu_hash.h:67-69,
+gpu_hash.cu:66-67,334-335): rank g owns bucket range g as a local table with gpuhash_geom_init_shard geometry and
+the results equal the single-table oracle's (tests/test_sharded_gloo.py, tests/test_gpu_sharded.py).
+
+Per batch and rank:   scatter by owner -> exchange -> local kernel -> (searches) exchange back -> gather.
+
+Two exchanges:
+  "collective"  torch.distributed all_to_all_single on packed buffers (NCCL on GPUs, gloo in the CPU tests).
+                Needs the split sizes on the host, i.e. one device->host sync per batch: the baseline.
+  "p2p"         the fused path: the scatter kernel stores each request straight into its owner's inbox over
+                NVLink, the lookup kernel stores each result straight into the origin's staging area (peer pointers
+                from CUDA IPC), sequence-numbered flags replace every host sync and every collective.
+
+torch is plumbing here (process group, NCCL, current stream); the kernels are megakv_b200/csrc/gpuhash_shard.cu.
+The device work sits behind a small backend object so that the choreography below can be exercised on CPU with
+a stand-in backend (tests only).
+"""
+import ctypes as C
+
+import numpy as np
+
+MAX_SHARDS = 8
+
+
+def log2_exact(n):
+    l = int(n).bit_length() - 1
+    if n < 1 or (1 << l) != n or l > 3:
+        raise ValueError("world size must be 1, 2, 4 or 8 (the alternate bucket keeps 3 top bits)")
+    return l
+
+
+class ShardPlan:
+    """Pure arithmetic of the partition (host side)."""
+
+    def __init__(self, mem_p_total, world):
+        self.mem_p_total, self.world, self.log2 = mem_p_total, world, log2_exact(world)
+        self.bits = mem_p_total - 6                                 # bucket-index bits of the logical table
+        self.hash_mask_total = (1 << self.bits) - 1
+        self.shift = self.bits - self.log2
+        self.mem_p_shard = mem_p_total - self.log2
+
+    def owner(self, hash_):
+        h = np.asarray(hash_, dtype=np.uint32)
+        return ((h & np.uint32(self.hash_mask_total)) >> np.uint32(self.shift)).astype(np.int64)
+
+
+class ShardedIndex:
+    """search / insert / delete on the sharded table.  Requests and results are torch tensors on the backend's
+    device: int32 [n, 2] (sig, hash) for searches, [n, 3] (sig, hash, loc) for inserts/deletes, results [n, 2]."""
+
+    def __init__(self, backend, plan, group=None, exchange="collective"):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.be, self.plan = backend, plan
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world == plan.world
+        self.exchange = exchange
+        self.seq = 0
+        if exchange == "p2p":
+            backend.p2p_setup(self)
+
+    # ---- collective exchange (baseline)
+    def _a2a_counts(self, counts):
+        recv = counts.new_empty(self.world)
+        self.dist.all_to_all_single(recv, counts[: self.world].contiguous(), group=self.group)
+        return recv
+
+    def _route(self, req, words, want_perm):
+        be = self.be
+        send, counts, perm = be.scatter(req, words, want_perm)          # send: [G, cap, words]
+        recv_counts = self._a2a_counts(counts)
+        cs, rs = counts[: self.world].tolist(), recv_counts.tolist()    # host sync: the cost of this path
+        packed = be.pack(send, cs)                                       # [sum(cs), words]
+        inbox = be.empty(sum(rs), words)
+        self.dist.all_to_all_single(inbox, packed, rs, cs, group=self.group)
+        return inbox, cs, rs, perm
+
+    def search(self, sel, out=None):
+        if self.exchange == "p2p":
+            return self.be.p2p_search(self, sel, out)
+        inbox, cs, rs, perm = self._route(sel, 2, True)
+        res = self.be.search_local(inbox, rs)                            # [sum(rs), 2]
+        back = self.be.empty(sum(cs), 2)
+        self.dist.all_to_all_single(back, res, cs, rs, group=self.group)
+        return self.be.gather(back, cs, perm, sel.shape[0])
+
+    def insert(self, iel):
+        if self.exchange == "p2p":
+            return self.be.p2p_update(self, iel, insert=True)
+        inbox, cs, rs, _ = self._route(iel, 3, False)
+        self.be.insert_local(inbox, rs)
+
+    def delete(self, iel):
+        if self.exchange == "p2p":
+            return self.be.p2p_update(self, iel, insert=False)
+        inbox, cs, rs, _ = self._route(iel, 3, False)
+        return self.be.delete_local(inbox, rs)
+
+
+class CudaShardBackend:
+    """The product backend: buffers are torch CUDA tensors (plumbing), work is libgpuhash kernels on torch's
+    current stream.  `cap` = largest batch per rank."""
+
+    def __init__(self, plan, rank, cap, algo=0, layout=0, device=None):
+        import torch
+        from . import _native as N
+        from .hashindex import DeviceBuffer, make_geom
+        self.torch, self.N, self.L = torch, N, N.lib()
+        self.plan, self.rank, self.cap, self.G = plan, rank, int(cap), plan.world
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.geom = make_geom(plan.mem_p_total, algo, plan.log2, layout)
+        self.table = DeviceBuffer(self.L.gpuhash_table_bytes(C.byref(self.geom)), zero=True)
+        i32 = torch.int32
+        self.send = torch.empty((self.G, self.cap, 3), dtype=i32, device=self.dev)      # widest element
+        self.counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
+        self.perm = torch.empty((self.G, self.cap), dtype=i32, device=self.dev)
+        self.seg_counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
+        self.seg_ptrs_d = torch.zeros(MAX_SHARDS, dtype=torch.int64, device=self.dev)    # device array of region pointers
+        self.p2p = None
+
+    # -- helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _ptrs(values):
+        arr = (C.c_void_p * MAX_SHARDS)()
+        for k, v in enumerate(values):
+            arr[k] = v
+        return arr
+
+    def empty(self, n, words):
+        return self.torch.empty((max(n, 0), words), dtype=self.torch.int32, device=self.dev)
+
+    # -- collective path pieces
+    def scatter(self, req, words, want_perm):
+        n = req.shape[0]
+        assert n <= self.cap and req.is_contiguous() and req.dtype == self.torch.int32
+        base = self.send.data_ptr()
+        dst = self._ptrs([base + d * self.cap * words * 4 for d in range(self.G)])
+        self.N.check(self.L.gpuhash_route_scatter(req.data_ptr(), n, words, self.plan.hash_mask_total, self.plan.log2, dst,
+                                                  self.counts.data_ptr(), self.perm.data_ptr() if want_perm else None,
+                                                  self.cap, self._stream()), "gpuhash_route_scatter")
+        view = self.send.view(-1)[: self.G * self.cap * words].view(self.G, self.cap, words)
+        return view, self.counts, self.perm
+
+    def pack(self, send, cs):
+        return self.torch.cat([send[d, : cs[d]] for d in range(self.G)], dim=0).contiguous()
+
+    def _segments(self, buf, sizes, words):
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        ptrs = [buf.data_ptr() + int(offs[s]) * words * 4 for s in range(self.G)]
+        cnt = self.torch.tensor(list(sizes) + [0] * (MAX_SHARDS - self.G), dtype=self.torch.int32)
+        self.seg_counts.copy_(cnt, non_blocking=False)
+        return ptrs
+
+    def search_local(self, inbox, rs):
+        out = self.empty(sum(rs), 2)
+        if sum(rs):
+            self.N.check(self.L.gpuhash_search_segments(C.byref(self.geom), self.table.ptr, self.G,
+                                                        self._ptrs(self._segments(inbox, rs, 2)), self.seg_counts.data_ptr(),
+                                                        self._ptrs(self._segments(out, rs, 2)), sum(rs), None, 0, None,
+                                                        self._stream()), "gpuhash_search_segments")
+        return out
+
+    def gather(self, back, cs, perm, n):
+        out = self.empty(n, 2)
+        if n:
+            cnt = self.torch.tensor(list(cs) + [0] * (MAX_SHARDS - self.G), dtype=self.torch.int32, device=self.dev)
+            self.N.check(self.L.gpuhash_route_gather(self._ptrs(self._segments(back, cs, 2)), perm.data_ptr(), cnt.data_ptr(),
+                                                     self.cap, self.plan.log2, out.data_ptr(), n, None, 0, None,
+                                                     self._stream()), "gpuhash_route_gather")
+        return out
+
+    def insert_local(self, inbox, rs):
+        if sum(rs):
+            ptrs = self._segments(inbox, rs, 3)
+            self.seg_ptrs_d.copy_(self.torch.tensor(ptrs + [0] * (MAX_SHARDS - self.G), dtype=self.torch.int64))
+            self.N.check(self.L.gpuhash_insert_ex(C.byref(self.geom), self.table.ptr, self.seg_ptrs_d.data_ptr(),
+                                                  self.seg_counts.data_ptr(), self.G, None, 0, self._stream()), "gpuhash_insert_ex")
+
+    def delete_local(self, inbox, rs):
+        if sum(rs):
+            self.N.check(self.L.gpuhash_delete_segments(C.byref(self.geom), self.table.ptr, self.G,
+                                                        self._ptrs(self._segments(inbox, rs, 3)), self.seg_counts.data_ptr(),
+                                                        sum(rs), None, self._stream()), "gpuhash_delete_segments")
+
+    # -- fused path: symmetric arena per rank, exported over CUDA IPC
+    #    layout: inbox [G][cap][3] i32 | stage [G][cap][2] i32 | inbox_count [8] | req_flag [8] | res_flag [8] | err [8]
+    def p2p_setup(self, ix):
+        from .hashindex import DeviceBuffer
+        t, L, N = self.torch, self.L, self.N
+        G, cap = self.G, self.cap
+        self.off_inbox, self.off_stage = 0, G * cap * 12
+        self.off_cnt = self.off_stage + G * cap * 8
+        self.off_reqf, self.off_resf, self.off_err = self.off_cnt + 32, self.off_cnt + 64, self.off_cnt + 96
+        self.arena = DeviceBuffer(self.off_cnt + 128, zero=True)
+        handle = (C.c_ubyte * 64)()
+        N.check(L.gpuhash_ipc_export(self.arena.ptr, handle), "cudaIpcGetMemHandle")
+        mine = t.tensor(list(handle), dtype=t.uint8, device=self.dev)
+        allh = [t.empty_like(mine) for _ in range(G)]
+        ix.dist.all_gather(allh, mine, group=ix.group)
+        self.peer = []
+        for r in range(G):
+            if r == self.rank:
+                self.peer.append(self.arena.ptr)
+            else:
+                raw = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                p = L.gpuhash_ipc_import(raw)
+                if not p:
+                    raise N.GpuHashError(f"cudaIpcOpenMemHandle failed for rank {r}")
+                self.peer.append(p)
+        ix.dist.barrier(group=ix.group)
+        # constant pointer tables of the fused path
+        G, cap, r = self.G, self.cap, self.rank
+        self.pp_peer_inbox = self._ptrs([self.peer[d] + self.off_inbox + r * cap * 12 for d in range(G)])
+        self.pp_peer_cnt = self._ptrs([self.peer[d] + self.off_cnt for d in range(G)])
+        self.pp_peer_reqf = self._ptrs([self.peer[d] + self.off_reqf for d in range(G)])
+        self.pp_peer_resf = self._ptrs([self.peer[d] + self.off_resf for d in range(G)])
+        self.pp_my_inbox = self._ptrs([self.arena.ptr + self.off_inbox + s_ * cap * 12 for s_ in range(G)])
+        self.pp_origin_stage = self._ptrs([self.peer[s_] + self.off_stage + r * cap * 8 for s_ in range(G)])
+        self.pp_my_stage = self._ptrs([self.arena.ptr + self.off_stage + d * cap * 8 for d in range(G)])
+        self.seg_ptrs_d.copy_(t.tensor([self.arena.ptr + self.off_inbox + s_ * cap * 12 for s_ in range(G)]
+                                       + [0] * (MAX_SHARDS - G), dtype=t.int64))
+        t.cuda.synchronize()
+        self.p2p = True
+
+    def _p2p_scatter(self, ix, req, words, want_perm):
+        """requests -> owners' inboxes (my region of each), counts + flag published to every owner"""
+        L, N, st = self.L, self.N, self._stream()
+        n = req.shape[0]
+        ix.seq += 1
+        N.check(L.gpuhash_route_scatter(req.data_ptr(), n, words, self.plan.hash_mask_total, self.plan.log2,
+                                        self.pp_peer_inbox, self.counts.data_ptr(),
+                                        self.perm.data_ptr() if want_perm else None, self.cap, st), "gpuhash_route_scatter")
+        N.check(L.gpuhash_route_publish(self.counts.data_ptr(), self.plan.log2, self.rank, self.pp_peer_cnt,
+                                        self.pp_peer_reqf, ix.seq, st), "gpuhash_route_publish")
+        # everything enqueued after this sees what all sources published for batch ix.seq
+        N.check(L.gpuhash_wait_flags(self.arena.ptr + self.off_reqf, self.G, ix.seq, self.arena.ptr + self.off_err, st),
+                "gpuhash_wait_flags")
+
+    def p2p_search(self, ix, sel, out=None):
+        L, N, st = self.L, self.N, self._stream()
+        n = sel.shape[0]
+        self._p2p_scatter(ix, sel, 2, True)
+        N.check(L.gpuhash_search_segments(C.byref(self.geom), self.table.ptr, self.G, self.pp_my_inbox,
+                                          self.arena.ptr + self.off_cnt, self.pp_origin_stage, self.G * self.cap,
+                                          None, 0, None, st), "gpuhash_search_segments")
+        N.check(L.gpuhash_results_publish(self.plan.log2, self.rank, self.pp_peer_resf, ix.seq, st), "gpuhash_results_publish")
+        if out is None:
+            out = self.empty(n, 2)
+        N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), self.counts.data_ptr(), self.cap,
+                                       self.plan.log2, out.data_ptr(), max(n, 1), self.arena.ptr + self.off_resf, ix.seq,
+                                       self.arena.ptr + self.off_err, st), "gpuhash_route_gather")
+        return out
+
+    def p2p_update(self, ix, iel, insert):
+        L, N, st = self.L, self.N, self._stream()
+        self._p2p_scatter(ix, iel, 3, False)
+        if insert:
+            N.check(L.gpuhash_insert_ex(C.byref(self.geom), self.table.ptr, self.seg_ptrs_d.data_ptr(),
+                                        self.arena.ptr + self.off_cnt, self.G, None, 0, st), "gpuhash_insert_ex")
+        else:
+            N.check(L.gpuhash_delete_segments(C.byref(self.geom), self.table.ptr, self.G, self.pp_my_inbox,
+                                              self.arena.ptr + self.off_cnt, self.G * self.cap, None, st),
+                    "gpuhash_delete_segments")
+        # the inbox may be overwritten by the sources' next batch only after this rank has consumed it: raise the
+        # result flags too, and make the sources wait on them before they go on
+        N.check(L.gpuhash_results_publish(self.plan.log2, self.rank, self.pp_peer_resf, ix.seq, st), "gpuhash_results_publish")
+        N.check(L.gpuhash_wait_flags(self.arena.ptr + self.off_resf, self.G, ix.seq, self.arena.ptr + self.off_err, st),
+                "gpuhash_wait_flags")
+
+    def p2p_error(self):
+        """1 if a flag wait timed out (a peer died); checked by the callers after synchronising"""
+        return int(self.arena.download(np.uint32)[self.off_err // 4])

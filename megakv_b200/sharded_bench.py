@@ -1,0 +1,175 @@
+"""N > 1 arm of bench.py: the sharded index (BASELINE.json configs[4]).
+
+Weak scaling: every rank owns one 2^mem_p-byte shard (logical table 2^(mem_p + log2 N) bytes, preloaded to load
+factor 0.25 through the routed insert path itself) and issues its own batch of 65 536 requests per step
+(62 259 searches for keys drawn uniformly from the WHOLE population -> (N-1)/N of them leave the GPU, + 3 277
+inserts of fresh keys).  Both exchanges are inside the timed region.  The fused path (peer stores over NVLink +
+flags, no host sync, the K steps replayed as one CUDA graph) is the product; the same steps through NCCL
+all_to_all_single are timed next to it as `nccl_baseline`.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+BATCH, N_SEARCH = 65536, 62259
+N_INSERT = BATCH - N_SEARCH
+SEED = 1
+
+
+def main(args, rank, world, local_rank, log):
+    import torch
+    import torch.distributed as dist
+    import megakv_b200 as mk
+    from megakv_b200 import _native as N
+    from megakv_b200.sharded import ShardPlan, ShardedIndex, CudaShardBackend
+    import bench as B
+
+    torch.cuda.set_device(local_rank)
+    N.check(mk.lib().gpuhash_set_device(local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = mk.lib()
+    dev = torch.device("cuda", local_rank)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    mem_p_shard = args.mem_p
+    free, total = C.c_size_t(), C.c_size_t()
+    N.check(L.gpuhash_device_info(local_rank, None, None, C.byref(free), C.byref(total)))
+    while (1 << mem_p_shard) + (12 << 30) > free.value and mem_p_shard > 26:
+        mem_p_shard -= 1
+    log2w = world.bit_length() - 1
+    plan = ShardPlan(min(mem_p_shard + log2w, 38), world)
+    cap = 1 << 20
+    be = CudaShardBackend(plan, rank, cap)
+    ix = ShardedIndex(be, plan, exchange="p2p")
+    ixc = ShardedIndex(be, plan, exchange="collective")          # same table, NCCL exchange (baseline)
+
+    # ---- preload through the routed insert path: rank r inserts key indices r, r + world, ... in chunks
+    pop = (1 << plan.mem_p_total) // 8 // 4
+    per_rank = pop // world
+    gen = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    t0 = time.time()
+    for first in range(0, per_rank, cap):
+        n = min(cap, per_rank - first)
+        N.check(L.gpuhash_gen_inserts(gen.data_ptr(), None, SEED, rank * per_rank + first, n, be._stream()))
+        ix.insert(gen[:n])
+    torch.cuda.synchronize(); dist.barrier()
+    log(f"preloaded {pop} keys over {world} shards in {time.time() - t0:.2f} s (p2p err={be.p2p_error()})")
+
+    # ---- resident batches
+    kd = min(steps + warm, 2048)
+    sel = torch.empty((kd, N_SEARCH, 2), dtype=torch.int32, device=dev)
+    ins = torch.empty((kd, N_INSERT, 3), dtype=torch.int32, device=dev)
+    out = torch.empty((kd, N_SEARCH, 2), dtype=torch.int32, device=dev)
+    N.check(L.gpuhash_gen_queries(sel.data_ptr(), None, SEED, per_rank * world, N_SEARCH * kd, 99 + rank, 0.0, 0.0, be._stream()))
+    N.check(L.gpuhash_gen_inserts(ins.data_ptr(), None, SEED, pop + rank * (1 << 26), N_INSERT * kd, be._stream()))
+    torch.cuda.synchronize()
+
+    def run_steps(index, first, count, with_insert=True):
+        for i in range(count):
+            b = (first + i) % kd
+            index.search(sel[b], out[b])
+            if with_insert:
+                index.insert(ins[b])
+
+    def timed(index, first, count, graph, with_insert=True):
+        """seconds for `count` steps, max over ranks"""
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run_steps(index, first, count, with_insert)
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record(); g.replay(); e1.record()
+        else:
+            e0.record(); run_steps(index, first, count, with_insert); e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    use_graph = bool(args.graph)
+    try:
+        timed(ix, 0, warm, use_graph)                                   # warm-up
+    except Exception as e:                                              # graph capture is an optimisation, not a dependency
+        log(f"graph capture failed ({e}); running eagerly")
+        use_graph = False
+        timed(ix, 0, warm, False)
+    sampler = B.ClockSampler(local_rank)
+    with sampler:
+        t_val = timed(ix, warm, steps, use_graph)
+    value = world * steps * BATCH / t_val / 1e6
+    err = be.p2p_error()
+    assert err == 0, "a flag wait timed out"
+    chk = out[(warm + steps - 1) % kd].cpu().numpy().view(np.uint32)
+    hit = float(((chk[:, 0] != 0) | (chk[:, 1] != 0)).mean())
+    assert hit > 0.999, f"searches did not hit: {hit}"
+
+    with sampler:
+        t_s = timed(ix, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
+    # NCCL baseline on fewer steps (host sync per exchange)
+    kb = min(steps, 200)
+    timed(ixc, 0, 3, False)
+    t_nccl = timed(ixc, warm, kb, False)
+
+    # e2e: pinned host -> device -> routed lookup -> pinned host, every step
+    ke = min(steps, 512)
+    hs = torch.empty((ke, N_SEARCH, 2), dtype=torch.int32).pin_memory(); hs.copy_(sel[:ke].cpu())
+    hi = torch.empty((ke, N_INSERT, 3), dtype=torch.int32).pin_memory()
+    N.check(L.gpuhash_gen_inserts(ins.data_ptr(), None, SEED, pop + rank * (1 << 26) + N_INSERT * kd, N_INSERT * ke, be._stream()))
+    hi.copy_(ins[:ke].cpu())
+    ho = torch.empty((ke, N_SEARCH, 2), dtype=torch.int32).pin_memory()
+    ds = torch.empty((2, N_SEARCH, 2), dtype=torch.int32, device=dev); di = torch.empty((2, N_INSERT, 3), dtype=torch.int32, device=dev)
+    do = torch.empty((2, N_SEARCH, 2), dtype=torch.int32, device=dev)
+
+    def e2e(count):
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(count):
+            k, b = i % 2, i % ke
+            ds[k].copy_(hs[b], non_blocking=True); di[k].copy_(hi[b], non_blocking=True)
+            ix.search(ds[k], do[k]); ix.insert(di[k])
+            ho[b].copy_(do[k], non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    e2e(min(ke, 20))
+    with sampler:
+        t_e = e2e(steps if steps <= ke else ke)
+    e_steps = steps if steps <= ke else ke
+    e2e_val = world * e_steps * BATCH / t_e / 1e6
+
+    if rank == 0:
+        peak, peak_src = B.peaks()
+        bytes_per_search = 8 + 2 * 32 + 32 * 1.0 + 8
+        achieved = steps * N_SEARCH * bytes_per_search / t_s / 1e9      # per GPU
+        cfg = B.workload_config(plan.mem_p_shard, args)
+        cfg["workload"] = (f"configs[4]: {world}xB200 sharded index, logical table 2^{plan.mem_p_total} bytes "
+                           f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
+                           f"per GPU and step {N_SEARCH} searches + {N_INSERT} inserts")
+        cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph,
+                    "parallelism": f"shard{world}"})
+        line = {
+            "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)", "value": round(value, 1), "unit": "Mops/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(t_val / steps * 1e3, 6),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
+                    "d2h_bytes_per_step": 8 * N_SEARCH, "steps": e_steps},
+            "gpu_launches": steps * 12,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "kernel": "search_segments_kernel (per GPU, routed)", "peak_source": peak_src,
+                         "note": "search path only, includes both NVLink exchanges"},
+            "nccl_baseline": {"value": round(world * kb * BATCH / t_nccl / 1e6, 1), "unit": "Mops/s", "steps": kb,
+                              "what": "same steps, exchanges through torch.distributed all_to_all_single"},
+            "cpu_baseline": None, "clocks": sampler.summary(), "search_hit_fraction": round(hit, 5),
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -1,0 +1,87 @@
+"""GPU suite, needs >= 2 devices: the sharded index with real kernels, both exchanges, against the single-table
+oracle of the logical table.  Skipped on a 1-GPU box (the CPU suite covers the routing logic over gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, exchange, ret):
+    import torch
+    import torch.distributed as dist
+    import megakv_b200 as mk
+    from megakv_b200.sharded import ShardPlan, ShardedIndex, CudaShardBackend
+    from oracle import pyoracle as po
+    from tests import helpers as H
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank); mk.lib().gpuhash_set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        mem_p, n = 24, 50000
+        plan = ShardPlan(mem_p, world)
+        be = CudaShardBackend(plan, rank, cap=1 << 17)
+        ix = ShardedIndex(be, plan, exchange=exchange)
+        rng = np.random.default_rng(4242)
+        allk = H.random_requests(rng, world * n)
+        mine = allk[rank * n:(rank + 1) * n]
+        ref = po.Oracle(mem_p); ref.insert(allk)
+        dev = torch.device("cuda", rank)
+
+        def t3(a):
+            return torch.from_numpy(np.ascontiguousarray(a).view(np.uint32).reshape(-1, 3).view(np.int32).copy()).to(dev)
+
+        def t2(a):
+            return torch.from_numpy(np.ascontiguousarray(H.to_sel(a)).view(np.uint32).reshape(-1, 2).view(np.int32).copy()).to(dev)
+
+        for part in np.array_split(mine, 3):
+            ix.insert(t3(part))
+        for rep in range(3):                                      # several batches back to back: buffer reuse + flags
+            probe = np.concatenate([allk[(rank + rep)::5], H.random_requests(rng, 1000 + 17 * rank)])
+            got = ix.search(t2(probe)).cpu().numpy().view(np.uint32)
+            want = ref.search(H.to_sel(probe)).reshape(-1, 2)
+            assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"search mismatch ({exchange}, rep {rep})"
+        assert ix.search(t2(allk[:0])).shape[0] == 0
+        victim = allk[((rank + 1) % world) * n:((rank + 1) % world) * n + 3000]
+        ix.delete(t3(victim))
+        torch.cuda.synchronize(); dist.barrier()
+        assert not ix.search(t2(victim)).cpu().numpy().any()
+        for r in range(world):
+            ref.delete(allk[((r + 1) % world) * n:((r + 1) % world) * n + 3000])
+        # shard tables, concatenated in rank order, equal the logical table bucket for bucket (as multisets)
+        t = mk.DeviceTable.__new__(mk.DeviceTable); t.geom, t.ptr, t.nbytes = be.geom, be.table.ptr, be.table.nbytes
+        shard = torch.from_numpy(t.dump_reference().view(np.int32).copy()).to(dev)
+        t.ptr = None
+        parts = [torch.empty_like(shard) for _ in range(world)]
+        dist.all_gather(parts, shard)
+        whole = np.concatenate([p.cpu().numpy().view(np.uint32) for p in parts])
+        assert ref.digest(table=whole) == ref.digest()
+        if exchange == "p2p":
+            assert be.p2p_error() == 0
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["collective", "p2p"])
+def test_sharded_two_gpus(gpu, exchange):
+    if gpu.lib().gpuhash_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, exchange, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0, "a rank failed"
+    assert sorted(ret.keys()) == [0, 1]
