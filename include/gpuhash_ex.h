@@ -135,6 +135,8 @@ int    gpuhash_index_load(gpuhash_index_t *ix, const void *table_h);   /* host i
 int    gpuhash_index_dump(gpuhash_index_t *ix, void *table_h);         /* (converted to/from the device layout)     */
 int    gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset);
 int    gpuhash_index_enable_stats(gpuhash_index_t *ix, int on);
+/* on: gpuhash_index_submit's host buffers are PINNED and the kernels access them directly over PCIe (no staging copies) */
+int    gpuhash_index_set_zero_copy(gpuhash_index_t *ix, int on);
 
 /* One scheduler cycle for one worker with HOST buffers (pinned or pageable), in the reference's order
  * search -> delete -> insert on the worker's stream (mega_scheduler.c:392-502).  Asynchronous: results
@@ -208,7 +210,7 @@ int gpuhash_bench_resident(const gpuhash_geom_t *g, void *table_d,
 int gpuhash_bench_e2e(gpuhash_index_t *ix,
 		const void *search_h, size_t n_search, void *out_h,
 		const void *insert_h, size_t n_insert,
-		int steps, gpuhash_bench_result_t *res);
+		int steps, int use_graph, gpuhash_bench_result_t *res);
 
 #ifdef __cplusplus
 }

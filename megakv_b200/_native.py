@@ -98,6 +98,7 @@ SYMBOLS = {
     "gpuhash_index_dump": (_i, [_vp, _vp]),
     "gpuhash_index_stats": (_i, [_vp, _sp, _i]),
     "gpuhash_index_enable_stats": (_i, [_vp, _i]),
+    "gpuhash_index_set_zero_copy": (_i, [_vp, _i]),
     "gpuhash_index_submit": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gpuhash_index_sync": (_i, [_vp]),
     "gpuhash_route_scatter": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -113,7 +114,7 @@ SYMBOLS = {
     "gpuhash_gen_inserts": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, _vp]),
     "gpuhash_gen_queries": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
     "gpuhash_bench_resident": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),
-    "gpuhash_bench_e2e": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, C.POINTER(BenchResult)]),
+    "gpuhash_bench_e2e": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, C.POINTER(BenchResult)]),
 }
 
 _lib = None

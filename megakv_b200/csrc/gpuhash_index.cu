@@ -37,6 +37,7 @@ struct gpuhash_index_s {
 	void *insert_in_d[MAX_WORKERS];
 	gpuhash_stats_t *stats_d;
 	int stats_on;
+	int zero_copy;       /* kernels read requests from / write results to the caller's pinned host buffers directly */
 };
 
 extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
@@ -137,6 +138,11 @@ extern "C" int gpuhash_index_dump(gpuhash_index_t *ix, void *table_h)
 
 extern "C" int gpuhash_index_enable_stats(gpuhash_index_t *ix, int on) { ix->stats_on = on != 0; return 0; }
 
+/* Zero-copy mode: the host buffers handed to gpuhash_index_submit must be pinned (cudaHostAlloc / cudaHostRegister,
+ * like the reference's batch buffers, mega_recv.c:154-156,176).  The kernels then read the requests and write the
+ * results over PCIe themselves: no staging copy, no copy-engine call, one launch per non-empty part of the batch. */
+extern "C" int gpuhash_index_set_zero_copy(gpuhash_index_t *ix, int on) { ix->zero_copy = on != 0; return 0; }
+
 extern "C" int gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset)
 {
 	cudaError_t e = cudaDeviceSynchronize();
@@ -157,6 +163,12 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 	gpuhash_stats_t *st = ix->stats_on ? ix->stats_d : NULL;
 	cudaError_t e;
 	int rc;
+	if (ix->zero_copy) {
+		if (n_search && (rc = gpuhash_search_ex(&ix->geom, search_in_h, search_out_h, ix->table, n_search, st, s)) != 0) return rc;
+		if (n_delete && (rc = gpuhash_delete_ex(&ix->geom, delete_in_h, ix->table, n_delete, st, 0, s)) != 0) return rc;
+		if (n_insert && (rc = gpuhash_insert_flat_ex(&ix->geom, ix->table, insert_in_h, n_insert, st, 0, s)) != 0) return rc;
+		return 0;
+	}
 	if (n_search) {                                                            /* mega_scheduler.c:393-420 */
 		if ((e = cudaMemcpyAsync(ix->search_in_d[w], search_in_h, n_search * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
 		if ((rc = gpuhash_search_ex(&ix->geom, ix->search_in_d[w], ix->search_out_d[w], ix->table, n_search, st, s)) != 0) return rc;
@@ -255,35 +267,54 @@ extern "C" int gpuhash_bench_resident(const gpuhash_geom_t *g, void *table_d,
 
 /* K cycles through the host-buffer API.  Cycle i uses worker slot i % workers and the i-th batch of the
  * pinned arrays (search_h: steps*n_search selem_t, out_h: steps*2*n_search loc_t, insert_h: steps*n_insert
- * ielem_t), so every step moves its own bytes over PCIe in both directions inside the timed region. */
+ * ielem_t), so every step moves its own bytes over PCIe in both directions inside the timed region.
+ * use_graph: the submits are captured once into a CUDA graph (copies and kernels become graph nodes) and the
+ * graph launch is timed -- what a scheduler with fixed pinned batch buffers would replay every cycle. */
 extern "C" int gpuhash_bench_e2e(gpuhash_index_t *ix,
 		const void *search_h, size_t n_search, void *out_h,
 		const void *insert_h, size_t n_insert,
-		int steps, gpuhash_bench_result_t *res)
+		int steps, int use_graph, gpuhash_bench_result_t *res)
 {
 	if (!ix || !res || steps < 1) return -1;
 	memset(res, 0, sizeof *res);
 	cudaStream_t main_s;
-	cudaEvent_t ev_start, ev_stop, ev_done[MAX_WORKERS];
+	cudaEvent_t ev_start, ev_stop, ev_done[MAX_WORKERS], fork;
 	cudaStreamCreateWithFlags(&main_s, cudaStreamNonBlocking);
-	cudaEventCreate(&ev_start); cudaEventCreate(&ev_stop);
+	cudaEventCreate(&ev_start); cudaEventCreate(&ev_stop); cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
 	for (int k = 0; k < ix->workers; k++) cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming);
-	cudaDeviceSynchronize();
-	cudaEventRecord(ev_start, main_s);
-	for (int k = 0; k < ix->workers; k++) cudaStreamWaitEvent(ix->stream[k], ev_start, 0);
+	cudaGraph_t graph = NULL; cudaGraphExec_t gexec = NULL;
+	cudaError_t e = cudaSuccess;
 	int rc = 0;
-	for (int i = 0; i < steps && rc == 0; i++)
-		rc = gpuhash_index_submit(ix, i % ix->workers,
-				(const char *)search_h + (size_t)i * n_search * 8, n_search, (char *)out_h + (size_t)i * n_search * 8,
-				NULL, 0,
-				(const char *)insert_h + (size_t)i * n_insert * 12, n_insert);
-	for (int k = 0; k < ix->workers; k++) { cudaEventRecord(ev_done[k], ix->stream[k]); cudaStreamWaitEvent(main_s, ev_done[k], 0); }
-	cudaEventRecord(ev_stop, main_s);
-	cudaError_t e = cudaEventSynchronize(ev_stop);
-	if (e == cudaSuccess) cudaEventElapsedTime(&res->total_ms, ev_start, ev_stop);
 	cudaDeviceSynchronize();
+	if (use_graph) e = cudaStreamBeginCapture(main_s, cudaStreamCaptureModeThreadLocal);
+	else cudaEventRecord(ev_start, main_s);
+	if (e == cudaSuccess) {
+		cudaEventRecord(fork, main_s);
+		for (int k = 0; k < ix->workers; k++) cudaStreamWaitEvent(ix->stream[k], fork, 0);
+		for (int i = 0; i < steps && rc == 0; i++)
+			rc = gpuhash_index_submit(ix, i % ix->workers,
+					(const char *)search_h + (size_t)i * n_search * 8, n_search, (char *)out_h + (size_t)i * n_search * 8,
+					NULL, 0,
+					(const char *)insert_h + (size_t)i * n_insert * 12, n_insert);
+		for (int k = 0; k < ix->workers; k++) { cudaEventRecord(ev_done[k], ix->stream[k]); cudaStreamWaitEvent(main_s, ev_done[k], 0); }
+		if (use_graph) {
+			e = cudaStreamEndCapture(main_s, &graph);
+			if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&gexec, graph, 0);
+			if (e == cudaSuccess && rc == 0) {
+				cudaDeviceSynchronize();
+				cudaEventRecord(ev_start, main_s);
+				e = cudaGraphLaunch(gexec, main_s);
+			}
+		}
+		cudaEventRecord(ev_stop, main_s);
+	}
+	if (e == cudaSuccess && rc == 0) e = cudaEventSynchronize(ev_stop);
+	if (e == cudaSuccess && rc == 0) cudaEventElapsedTime(&res->total_ms, ev_start, ev_stop);
+	cudaDeviceSynchronize();
+	if (gexec) cudaGraphExecDestroy(gexec);
+	if (graph) cudaGraphDestroy(graph);
 	for (int k = 0; k < ix->workers; k++) cudaEventDestroy(ev_done[k]);
-	cudaStreamDestroy(main_s); cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop);
+	cudaStreamDestroy(main_s); cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(fork);
 	res->launches = (unsigned long long)steps * ((n_search ? 1 : 0) + (n_insert ? 1 : 0));
 	res->search_ops = (unsigned long long)steps * n_search;
 	res->insert_ops = (unsigned long long)steps * n_insert;

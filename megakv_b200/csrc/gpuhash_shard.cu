@@ -274,9 +274,9 @@ extern "C" int gpuhash_route_gather(const void *const *staged_ptrs, const uint32
 {
 	const int G = 1 << log2_shards;
 	Ptrs S;
-	if (fill_ptrs(S, staged_ptrs, G) || !perm_d || !counts_d || !out_d) return -1;
+	if (fill_ptrs(S, staged_ptrs, G) || !perm_d || !counts_d || (n && !out_d)) return -1;
 	if (wait_seq && (!flags_d || !err_d)) return -1;
-	if (n == 0) return 0;
+	if (n == 0 && !wait_seq) return 0;                       /* with a flag wait the (empty) kernel still orders the stream */
 	route_gather_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(S, perm_d, counts_d, cap, G, (uint2 *)out_d, flags_d, wait_seq, err_d);
 	return (int)cudaGetLastError();
 }

@@ -104,7 +104,7 @@ class CudaShardBackend:
     """The product backend: buffers are torch CUDA tensors (plumbing), work is libgpuhash kernels on torch's
     current stream.  `cap` = largest batch per rank."""
 
-    def __init__(self, plan, rank, cap, algo=0, layout=0, device=None):
+    def __init__(self, plan, rank, cap, algo=0, layout=0, device=None, table=None):
         import torch
         from . import _native as N
         from .hashindex import DeviceBuffer, make_geom
@@ -112,7 +112,8 @@ class CudaShardBackend:
         self.plan, self.rank, self.cap, self.G = plan, rank, int(cap), plan.world
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.geom = make_geom(plan.mem_p_total, algo, plan.log2, layout)
-        self.table = DeviceBuffer(self.L.gpuhash_table_bytes(C.byref(self.geom)), zero=True)
+        # several backends ("lanes": independent buffer sets for batches in flight) may share one shard table
+        self.table = table if table is not None else DeviceBuffer(self.L.gpuhash_table_bytes(C.byref(self.geom)), zero=True)
         i32 = torch.int32
         self.send = torch.empty((self.G, self.cap, 3), dtype=i32, device=self.dev)      # widest element
         self.counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
@@ -253,7 +254,7 @@ class CudaShardBackend:
         if out is None:
             out = self.empty(n, 2)
         N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), self.counts.data_ptr(), self.cap,
-                                       self.plan.log2, out.data_ptr(), max(n, 1), self.arena.ptr + self.off_resf, ix.seq,
+                                       self.plan.log2, out.data_ptr() if n else None, n, self.arena.ptr + self.off_resf, ix.seq,
                                        self.arena.ptr + self.off_err, st), "gpuhash_route_gather")
         return out
 

@@ -42,9 +42,14 @@ def main(args, rank, world, local_rank, log):
     log2w = world.bit_length() - 1
     plan = ShardPlan(min(mem_p_shard + log2w, 38), world)
     cap = 1 << 20
-    be = CudaShardBackend(plan, rank, cap)
+    be = CudaShardBackend(plan, rank, cap)                        # bulk lane: preload in 1 M-request batches
     ix = ShardedIndex(be, plan, exchange="p2p")
     ixc = ShardedIndex(be, plan, exchange="collective")          # same table, NCCL exchange (baseline)
+    # S lanes = S batches in flight per GPU, each with its own inboxes/staging/flags and stream (the sharded
+    # counterpart of the reference's one-stream-per-worker, mega_scheduler.c:276-280)
+    S = max(1, min(args.streams, 16))
+    lanes = [ShardedIndex(CudaShardBackend(plan, rank, BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
     # ---- preload through the routed insert path: rank r inserts key indices r, r + world, ... in chunks
     pop = (1 << plan.mem_p_total) // 8 // 4
@@ -68,11 +73,24 @@ def main(args, rank, world, local_rank, log):
     torch.cuda.synchronize()
 
     def run_steps(index, first, count, with_insert=True):
+        if index is not None:                                           # one lane, one stream (NCCL baseline)
+            for i in range(count):
+                b = (first + i) % kd
+                index.search(sel[b], out[b])
+                if with_insert:
+                    index.insert(ins[b])
+            return
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
         for i in range(count):
             b = (first + i) % kd
-            index.search(sel[b], out[b])
-            if with_insert:
-                index.insert(ins[b])
+            with torch.cuda.stream(streams[i % S]):
+                lanes[i % S].search(sel[b], out[b])
+                if with_insert:
+                    lanes[i % S].insert(ins[b])
+        for st in streams:
+            cur.wait_stream(st)
 
     def timed(index, first, count, graph, with_insert=True):
         """seconds for `count` steps, max over ranks"""
@@ -93,23 +111,23 @@ def main(args, rank, world, local_rank, log):
 
     use_graph = bool(args.graph)
     try:
-        timed(ix, 0, warm, use_graph)                                   # warm-up
+        timed(None, 0, warm, use_graph)                                 # warm-up
     except Exception as e:                                              # graph capture is an optimisation, not a dependency
         log(f"graph capture failed ({e}); running eagerly")
         use_graph = False
-        timed(ix, 0, warm, False)
+        timed(None, 0, warm, False)
     sampler = B.ClockSampler(local_rank)
     with sampler:
-        t_val = timed(ix, warm, steps, use_graph)
+        t_val = timed(None, warm, steps, use_graph)
     value = world * steps * BATCH / t_val / 1e6
-    err = be.p2p_error()
+    err = be.p2p_error() + sum(l.be.p2p_error() for l in lanes)
     assert err == 0, "a flag wait timed out"
     chk = out[(warm + steps - 1) % kd].cpu().numpy().view(np.uint32)
     hit = float(((chk[:, 0] != 0) | (chk[:, 1] != 0)).mean())
     assert hit > 0.999, f"searches did not hit: {hit}"
 
     with sampler:
-        t_s = timed(ix, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
+        t_s = timed(None, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
     # NCCL baseline on fewer steps (host sync per exchange)
     kb = min(steps, 200)
     timed(ixc, 0, 3, False)
@@ -122,18 +140,24 @@ def main(args, rank, world, local_rank, log):
     N.check(L.gpuhash_gen_inserts(ins.data_ptr(), None, SEED, pop + rank * (1 << 26) + N_INSERT * kd, N_INSERT * ke, be._stream()))
     hi.copy_(ins[:ke].cpu())
     ho = torch.empty((ke, N_SEARCH, 2), dtype=torch.int32).pin_memory()
-    ds = torch.empty((2, N_SEARCH, 2), dtype=torch.int32, device=dev); di = torch.empty((2, N_INSERT, 3), dtype=torch.int32, device=dev)
-    do = torch.empty((2, N_SEARCH, 2), dtype=torch.int32, device=dev)
+    ds = torch.empty((S, N_SEARCH, 2), dtype=torch.int32, device=dev); di = torch.empty((S, N_INSERT, 3), dtype=torch.int32, device=dev)
+    do = torch.empty((S, N_SEARCH, 2), dtype=torch.int32, device=dev)
 
     def e2e(count):
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
         for i in range(count):
-            k, b = i % 2, i % ke
-            ds[k].copy_(hs[b], non_blocking=True); di[k].copy_(hi[b], non_blocking=True)
-            ix.search(ds[k], do[k]); ix.insert(di[k])
-            ho[b].copy_(do[k], non_blocking=True)
+            k, b = i % S, i % ke
+            with torch.cuda.stream(streams[k]):
+                ds[k].copy_(hs[b], non_blocking=True); di[k].copy_(hi[b], non_blocking=True)
+                lanes[k].search(ds[k], do[k]); lanes[k].insert(di[k])
+                ho[b].copy_(do[k], non_blocking=True)
+        for st in streams:
+            cur.wait_stream(st)
         e1.record(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -153,7 +177,7 @@ def main(args, rank, world, local_rank, log):
         cfg["workload"] = (f"configs[4]: {world}xB200 sharded index, logical table 2^{plan.mem_p_total} bytes "
                            f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
                            f"per GPU and step {N_SEARCH} searches + {N_INSERT} inserts")
-        cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph,
+        cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph, "lanes": S,
                     "parallelism": f"shard{world}"})
         line = {
             "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)", "value": round(value, 1), "unit": "Mops/s",
