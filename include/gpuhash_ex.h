@@ -73,6 +73,8 @@ typedef struct gpuhash_tune_s {
 	                            -1 = 4 lanes x 128-bit loads (reference layout only; comparison kernel) */
 	int search_split_mode;   /* REFERENCE layout only: 0 = by table size, 1 = location word on hit only, 2 = whole buckets */
 	int insert_ctas_per_sm;  /* grid of the count-independent insert kernel */
+	int fused_cycle;         /* 1 (default): gpuhash_index_submit and the bench loops issue ONE launch per batch
+	                            (gpuhash_cycle_ex); 0: one launch per operation kind, like the reference */
 } gpuhash_tune_t;
 void   gpuhash_set_tuning(const gpuhash_tune_t *t);
 void   gpuhash_get_tuning(gpuhash_tune_t *t);
@@ -86,6 +88,16 @@ int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *i
 		gpuhash_stats_t *stats_d, unsigned flags, void *stream);
 int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_d, size_t n,
 		gpuhash_stats_t *stats_d, unsigned flags, void *stream);
+
+/* One launch for a whole scheduler cycle of one worker (mega_scheduler.c:392-502): all searches, then all deletes,
+ * then all inserts, ordered inside the kernel.  Inserts are either a flat batch (ielem_d, n_insert) or segments with
+ * device-side counts (blk_input_d, blk_elem_num_d, num_blks; then ielem_d = NULL, n_insert = 0).  Any part may be empty. */
+int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
+		const void *selem_d, size_t n_search, void *out_d,
+		const void *delem_d, size_t n_delete,
+		const void *ielem_d, size_t n_insert,
+		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
+		gpuhash_stats_t *stats_d, void *stream);
 
 /* ---- device / pinned memory and stream plumbing ---- */
 int   gpuhash_device_count(void);

@@ -33,7 +33,11 @@ class Stats(C.Structure):                     # gpuhash_stats_t
 
 
 class Tune(C.Structure):                      # gpuhash_tune_t
-    _fields_ = [("search_qpt", C.c_int), ("search_split_mode", C.c_int), ("insert_ctas_per_sm", C.c_int)]
+    _fields_ = [("search_qpt", C.c_int), ("search_split_mode", C.c_int), ("insert_ctas_per_sm", C.c_int),
+                ("fused_cycle", C.c_int)]
+
+    def __init__(self, search_qpt=0, search_split_mode=0, insert_ctas_per_sm=4, fused_cycle=1):
+        super().__init__(search_qpt, search_split_mode, insert_ctas_per_sm, fused_cycle)
 
 
 class BenchResult(C.Structure):               # gpuhash_bench_result_t
@@ -64,6 +68,7 @@ SYMBOLS = {
     "gpuhash_insert_ex": (_i, [_gp, _vp, _vp, _vp, _i, _vp, _u, _vp]),
     "gpuhash_insert_flat_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
     "gpuhash_delete_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "gpuhash_cycle_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _vp, _vp]),
     "gpuhash_device_count": (_i, []),
     "gpuhash_set_device": (_i, [_i]),
     "gpuhash_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),

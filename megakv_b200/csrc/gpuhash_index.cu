@@ -163,10 +163,23 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 	gpuhash_stats_t *st = ix->stats_on ? ix->stats_d : NULL;
 	cudaError_t e;
 	int rc;
+	gpuhash_tune_t tune; gpuhash_get_tuning(&tune);
 	if (ix->zero_copy) {
+		if (tune.fused_cycle)
+			return gpuhash_cycle_ex(&ix->geom, ix->table, search_in_h, n_search, search_out_h, delete_in_h, n_delete,
+					insert_in_h, n_insert, NULL, NULL, 0, st, s);
 		if (n_search && (rc = gpuhash_search_ex(&ix->geom, search_in_h, search_out_h, ix->table, n_search, st, s)) != 0) return rc;
 		if (n_delete && (rc = gpuhash_delete_ex(&ix->geom, delete_in_h, ix->table, n_delete, st, 0, s)) != 0) return rc;
 		if (n_insert && (rc = gpuhash_insert_flat_ex(&ix->geom, ix->table, insert_in_h, n_insert, st, 0, s)) != 0) return rc;
+		return 0;
+	}
+	if (tune.fused_cycle) {                                                    /* all uploads, ONE launch, the download */
+		if (n_search && (e = cudaMemcpyAsync(ix->search_in_d[w], search_in_h, n_search * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+		if (n_delete && (e = cudaMemcpyAsync(ix->delete_in_d[w], delete_in_h, n_delete * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+		if (n_insert && (e = cudaMemcpyAsync(ix->insert_in_d[w], insert_in_h, n_insert * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+		if ((rc = gpuhash_cycle_ex(&ix->geom, ix->table, ix->search_in_d[w], n_search, ix->search_out_d[w], ix->delete_in_d[w], n_delete,
+				ix->insert_in_d[w], n_insert, NULL, NULL, 0, st, s)) != 0) return rc;
+		if (n_search && (e = cudaMemcpyAsync(search_out_h, ix->search_out_d[w], n_search * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
 		return 0;
 	}
 	if (n_search) {                                                            /* mega_scheduler.c:393-420 */
@@ -197,9 +210,15 @@ static int issue_resident(const gpuhash_geom_t *g, void *table_d,
 		const char *search_d, size_t n_search, char *out_d, const char *insert_d, size_t n_insert,
 		int steps, cudaStream_t *st, int streams)
 {
+	gpuhash_tune_t tune; gpuhash_get_tuning(&tune);
 	for (int i = 0; i < steps; i++) {
 		cudaStream_t s = st[i % streams];
 		int rc;
+		if (tune.fused_cycle && n_search && n_insert) {
+			if ((rc = gpuhash_cycle_ex(g, table_d, search_d + (size_t)i * n_search * 8, n_search, out_d + (size_t)i * n_search * 8,
+					NULL, 0, insert_d + (size_t)i * n_insert * 12, n_insert, NULL, NULL, 0, NULL, s)) != 0) return rc;
+			continue;
+		}
 		if (n_search && (rc = gpuhash_search_ex(g, search_d + (size_t)i * n_search * 8, out_d + (size_t)i * n_search * 8,
 				table_d, n_search, NULL, s)) != 0) return rc;
 		if (n_insert && (rc = gpuhash_insert_flat_ex(g, table_d, insert_d + (size_t)i * n_insert * 12, n_insert,

@@ -643,6 +643,132 @@ search_quad_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 	}
 }
 
+/* ---- one launch per scheduler cycle: search -> delete -> insert ---- */
+
+// The reference issues three launches per worker and cycle, stream-ordered search -> delete -> insert
+// (mega_scheduler.c:392-502), and declares a fused gpu_delete_insert it never defines (libgpuhash.h:53-62).
+// Here the whole cycle of one worker is ONE launch.  CTAs [0, Bs) search, [Bs, Bs+Bd) delete, the rest insert;
+// a delete CTA starts only when all Bs search CTAs have finished, an insert CTA only when all search and delete
+// CTAs have (counters in global memory).  CTAs of a 1-D grid are dispatched in index order, so when a waiting CTA
+// is resident every CTA it waits for has been dispatched already and none of them waits on anything: no
+// deadlock.  Results equal the three stream-ordered launches; what is saved is two launches per batch, which at
+// 64 K requests per batch is more than the lookups themselves cost.
+struct CycleArgs {
+	const uint2* search_in; uint2* search_out; unsigned long long n_search;
+	const uint32_t* delete_in; unsigned long long n_delete;
+	const uint32_t* insert_in; unsigned long long n_insert;          // flat insert batch, or
+	const uint32_t* const* blk_input; const int* blk_elem_num; int num_blks;   // ... segments with device-side counts
+	unsigned int search_ctas, delete_ctas, insert_ctas;
+	unsigned int* counters;                                           // [4], zero on entry, zero again on exit
+};
+
+__device__ __forceinline__ void cycle_wait(const unsigned int* c, unsigned int target)
+{
+	if (threadIdx.x == 0) {
+		unsigned int v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+			if (v < target) __nanosleep(64);
+		} while (v < target);
+	}
+	__syncthreads();
+}
+
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+cycle_kernel(Bucket* table, Geom g, Stats* st, CycleArgs a)
+{
+	const unsigned int bid = blockIdx.x;
+	int phase;
+	if (bid < a.search_ctas) {                                       // ---- search: four lanes per request
+		phase = 0;
+		const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
+		const unsigned long long per_iter = ((unsigned long long)a.search_ctas * blockDim.x) >> 2;
+		const unsigned long long n = a.n_search, n_up = (n + 7) & ~7ULL;
+		for (unsigned long long i = ((unsigned long long)bid * blockDim.x + threadIdx.x) >> 2; i < n_up; i += per_iter) {
+			const bool live = i < n;
+			uint2 q = make_uint2(0u, 0u);
+			Row r;
+#pragma unroll
+			for (int k = 0; k < 8; k++) r.w[k] = 0;
+			if (live) {
+				q = ld_stream_u2(a.search_in + i);
+				const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
+				r = ld_row_ro(table[b].w + 8 * half);
+			}
+			uint32_t m, loc;
+			if (kPairs) {
+				m = (r.w[0] == q.x ? 1u : 0u) | (r.w[2] == q.x ? 2u : 0u) | (r.w[4] == q.x ? 4u : 0u) | (r.w[6] == q.x ? 8u : 0u);
+				loc = (m & 1u) ? r.w[1] : (m & 2u) ? r.w[3] : (m & 4u) ? r.w[5] : r.w[7];
+				if (!live) m = 0;
+				const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));
+				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
+				if (live && sub == 0) st_stream_u2(a.search_out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
+			} else {
+				m = live ? eq_mask(r, q.x) : 0u;
+				const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));
+				const int l = __ffs(msig | 0x100u) - 1 & 7;
+				loc = r.w[0];
+				if (l == 1) loc = r.w[1];
+				if (l == 2) loc = r.w[2];
+				if (l == 3) loc = r.w[3];
+				if (l == 4) loc = r.w[4];
+				if (l == 5) loc = r.w[5];
+				if (l == 6) loc = r.w[6];
+				if (l == 7) loc = r.w[7];
+				if (!msig) loc = 0;
+				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + 1);
+				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + 3);
+				if (live && sub == 0) st_stream_u2(a.search_out + i, make_uint2(l0, l1));
+			}
+		}
+	} else if (bid < a.search_ctas + a.delete_ctas) {                // ---- delete, after every search
+		phase = 1;
+		cycle_wait(a.counters + 0, a.search_ctas);
+		const unsigned long long stride = (unsigned long long)a.delete_ctas * blockDim.x;
+		for (unsigned long long i = (unsigned long long)(bid - a.search_ctas) * blockDim.x + threadIdx.x; i < a.n_delete; i += stride) {
+			int z = delete_one<kPairs>(table, g, ld_stream_u32(a.delete_in + 3 * i), ld_stream_u32(a.delete_in + 3 * i + 1),
+					ld_stream_u32(a.delete_in + 3 * i + 2));
+			if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+		}
+	} else {                                                         // ---- insert, after every search and delete
+		phase = 2;
+		cycle_wait(a.counters + 0, a.search_ctas);
+		cycle_wait(a.counters + 1, a.delete_ctas);
+		const unsigned int ib = bid - a.search_ctas - a.delete_ctas;
+		const unsigned long long stride = (unsigned long long)a.insert_ctas * blockDim.x;
+		if (a.blk_input) {
+			unsigned long long base = 0;                             // segments are few (INSERT_BLOCK = 8): walk them
+			for (int k = 0; k < a.num_blks; k++) {
+				const int c = a.blk_elem_num[k];
+				const unsigned long long cnt = c > 0 ? (unsigned long long)c : 0ULL;
+				const uint32_t* p = a.blk_input[k];
+				// element e of the concatenation belongs to thread (e mod stride)
+				unsigned long long first = (unsigned long long)ib * blockDim.x + threadIdx.x;
+				first = first >= base % stride ? first - base % stride : first + stride - base % stride;
+				for (unsigned long long e = first; e < cnt; e += stride)
+					insert_one<kPairs>(table, g, ld_stream_u32(p + 3 * e), ld_stream_u32(p + 3 * e + 1), ld_stream_u32(p + 3 * e + 2), st);
+				base += cnt;
+			}
+		} else {
+			for (unsigned long long i = (unsigned long long)ib * blockDim.x + threadIdx.x; i < a.n_insert; i += stride)
+				insert_one<kPairs>(table, g, ld_stream_u32(a.insert_in + 3 * i), ld_stream_u32(a.insert_in + 3 * i + 1),
+						ld_stream_u32(a.insert_in + 3 * i + 2), st);
+		}
+	}
+	// ---- this CTA is done: count it; the last CTA of the launch clears the counters for their next user
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(a.counters + phase, 1u);
+		if (atomicAdd(a.counters + 3, 1u) == gridDim.x - 1) {
+			a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0;
+			__threadfence();
+		}
+	}
+}
+
 /* ---- alternative search shape, kept for comparison (tools/sweep.py) ---- */
 
 __device__ __forceinline__ uint4 ld_half_row(const uint32_t* p)

@@ -39,7 +39,7 @@ static_assert(sizeof(gpuhash_stats_t) == sizeof(gh::Stats), "stats mirror");
 static gpuhash_geom_t g_default_geom = {
 	(uint32_t)HASH_MASK, (uint32_t)BLOCK_HASH_MASK, GH_DEFAULT_ALGO, 5u, GH_DEFAULT_LAYOUT
 };
-static gpuhash_tune_t g_tune = { 0, 0, 4 };
+static gpuhash_tune_t g_tune = { 0, 0, 4, 1 };
 
 static int g_sm_count[64];          /* 0 = not queried yet */
 static int g_l2_bytes[64];
@@ -266,6 +266,54 @@ extern "C" int gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, uns
 	return (int)cudaGetLastError();
 }
 
+/* One launch for a whole scheduler cycle of one worker: searches, then deletes, then inserts (flat batch with a
+ * host-known count, or -- blk_input_d != NULL -- segments with device-side counts).  Same results as
+ * gpuhash_search_ex, gpuhash_delete_ex, gpuhash_insert_*_ex issued in that order on one stream. */
+#define GH_CYCLE_SLOTS 4096
+static unsigned int *g_cycle_counters[64];        /* per device: GH_CYCLE_SLOTS x 4 words, zero */
+static unsigned int g_cycle_next[64];
+
+extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
+		const void *selem_d, size_t n_search, void *out_d,
+		const void *delem_d, size_t n_delete,
+		const void *ielem_d, size_t n_insert,
+		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
+		gpuhash_stats_t *stats_d, void *stream)
+{
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || !table_d) return -1;
+	if ((n_search && (!selem_d || !out_d)) || (n_delete && !delem_d) || (n_insert && !ielem_d)) return -1;
+	if (blk_input_d && (!blk_elem_num_d || num_blks < 1 || n_insert)) return -1;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+	if (!g_cycle_counters[dev]) {
+		cudaError_t e = cudaMalloc((void **)&g_cycle_counters[dev], GH_CYCLE_SLOTS * 4 * sizeof(unsigned int));
+		if (e != cudaSuccess) return (int)e;
+		if ((e = cudaMemset(g_cycle_counters[dev], 0, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
+	}
+	gh::CycleArgs a;
+	a.search_in = (const uint2 *)selem_d; a.search_out = (uint2 *)out_d; a.n_search = n_search;
+	a.delete_in = (const uint32_t *)delem_d; a.n_delete = n_delete;
+	a.insert_in = (const uint32_t *)ielem_d; a.n_insert = n_insert;
+	a.blk_input = (const uint32_t *const *)blk_input_d; a.blk_elem_num = blk_elem_num_d; a.num_blks = num_blks;
+	const size_t sms = (size_t)sm_count_now();
+	size_t sc = (n_search * 4 + 255) / 256, dc = (n_delete + 255) / 256, ic = (n_insert + 255) / 256;
+	if (sc > sms * 32) sc = sms * 32;
+	if (dc > sms * 8) dc = sms * 8;
+	if (ic > sms * 8) ic = sms * 8;
+	if (blk_input_d) ic = sms * (size_t)(g_tune.insert_ctas_per_sm > 0 ? g_tune.insert_ctas_per_sm : 4);
+	a.search_ctas = (unsigned)sc; a.delete_ctas = (unsigned)dc; a.insert_ctas = (unsigned)ic;
+	const unsigned total = a.search_ctas + a.delete_ctas + a.insert_ctas;
+	if (total == 0) return 0;
+	/* a counter slot is reused GH_CYCLE_SLOTS launches later; the launch that used it has cleared it long before */
+	a.counters = g_cycle_counters[dev] + 4 * (g_cycle_next[dev]++ % GH_CYCLE_SLOTS);
+	gh::Geom gg = to_geom(g);
+	if (gg.layout == gh::kLayoutPairs)
+		gh::cycle_kernel<true><<<total, 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, (gh::Stats *)stats_d, a);
+	else
+		gh::cycle_kernel<false><<<total, 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, (gh::Stats *)stats_d, a);
+	return (int)cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ legacy C ABI */
 
 /* reference gpu_hash.cu:482-518.  num_thread / threads_per_blk described the reference's own
@@ -309,10 +357,12 @@ extern "C" void gpu_delete_insert(bucket_t *hash_table, delem_t *delete_in, uint
 		uint32_t num_delete_thread, uint32_t threads_per_blk, cudaStream_t stream)
 {
 	(void)num_delete_thread; (void)threads_per_blk;
-	int rc = gpuhash_delete_ex(&g_default_geom, delete_in, hash_table, (size_t)num_delete_job, NULL, 0, (void *)stream);
-	assert(rc >= 0);
-	rc = gpuhash_insert_ex(&g_default_geom, hash_table, (const void *const *)insert_blk_input,
-			insert_blk_elem_num, num_insert_blks, NULL, 0, (void *)stream);
+	int rc;
+	if (num_insert_blks > 0)
+		rc = gpuhash_cycle_ex(&g_default_geom, hash_table, NULL, 0, NULL, delete_in, (size_t)num_delete_job, NULL, 0,
+				(const void *const *)insert_blk_input, insert_blk_elem_num, num_insert_blks, NULL, (void *)stream);
+	else
+		rc = gpuhash_delete_ex(&g_default_geom, delete_in, hash_table, (size_t)num_delete_job, NULL, 0, (void *)stream);
 	assert(rc >= 0); (void)rc;
 }
 

@@ -367,7 +367,7 @@ def test_insert_concurrent_high_load_invariants(gpu, layout, algo, rng):
     sel = H.to_sel(iel)
     found_gpu = (gpu_search(t, sel).reshape(-1, 2) == iel["loc"][:, None]).any(axis=1).sum()
     found_orc = (o.search(sel).reshape(-1, 2) == iel["loc"][:, None]).any(axis=1).sum()
-    assert abs(int(found_gpu) - int(found_orc)) <= 0.01 * len(iel)
+    assert abs(int(found_gpu) - int(found_orc)) <= 0.03 * len(iel)
 
 
 def test_insert_same_bucket_contention_keeps_pairs_intact(gpu, layout, rng):
@@ -414,10 +414,13 @@ def test_insert_duplicate_keys_in_one_batch(gpu, layout, rng):
 
 # ----------------------------------------------------------------------------- scheduler-cycle object
 
-def test_index_cycle_matches_oracle_in_reference_order(gpu, layout, rng):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_index_cycle_matches_oracle_in_reference_order(gpu, layout, fused, rng):
     """search -> delete -> insert inside one cycle (mega_scheduler.c:392-502): searches of a cycle do not
     see that cycle's inserts."""
     mem_p = 20
+    old = N.Tune(); N.lib().gpuhash_get_tuning(old)
+    N.lib().gpuhash_set_tuning(N.Tune(0, 0, 4, fused))              # one launch per cycle, or one per operation kind
     ix = mk.GpuHashIndex(mem_p, workers=2, max_search=1 << 16, max_insert=1 << 15, max_delete=1 << 15, layout=layout)
     o = po.Oracle(mem_p)
     live = H.random_requests(rng, 30000)
@@ -436,6 +439,30 @@ def test_index_cycle_matches_oracle_in_reference_order(gpu, layout, rng):
         assert o.digest(table=ix.dump()) == o.digest()
         live = np.concatenate([live[~np.isin(live["loc"], dele["loc"])], fresh])
     ix.close()
+    N.lib().gpuhash_set_tuning(old)
+
+
+def test_legacy_gpu_delete_insert_is_one_launch_with_both_effects(gpu, layout, rng):
+    """libgpuhash.h:53-62 declares gpu_delete_insert; the reference never defines it.  Here: delete batch, then the
+    8-segment insert batch (device-side counts), in one launch -- equal to gpu_hash_delete + gpu_hash_insert."""
+    import ctypes as C
+    mem_p = 20
+    t = mk.DeviceTable(mem_p, layout=layout); t.make_default()
+    o = po.Oracle(mem_p)
+    base = H.random_requests(rng, 40000)
+    gpu_insert(t, base); o.insert(base)
+    dele = base[rng.permutation(len(base))[:7000]]
+    fresh = H.random_requests(rng, 9000, loc_base=50001)
+    fresh[:100] = dele[:100]; fresh["loc"][:100] += 7                 # re-insert of keys deleted in the same call
+    blocks = mk.split_insert_blocks(fresh, 8); blocks[3] = blocks[3][:0]
+    segs = mk.InsertSegments(blocks)
+    del_d = mk.DeviceBuffer.from_host(dele)
+    N.lib().gpu_delete_insert(t.ptr, del_d.ptr, len(dele), segs.ptrs.ptr, segs.nums.ptr, 8, 16384, 256, None)
+    mk.device_sync()
+    o.delete(dele); o.insert_blocks(blocks)
+    assert o.digest(table=t.dump_reference()) == o.digest()
+    sel = H.to_sel(np.concatenate([base, fresh]))
+    assert np.array_equal(np.sort(gpu_search(t, sel).reshape(-1, 2), 1), np.sort(o.search(sel).reshape(-1, 2), 1))
 
 
 # ----------------------------------------------------------------------------- full size (BASELINE config 2)
