@@ -89,6 +89,10 @@ int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *i
 int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_d, size_t n,
 		gpuhash_stats_t *stats_d, unsigned flags, void *stream);
 
+/* Allocates the library's small per-device state now instead of at first use (needed before capturing launches into a
+ * CUDA graph; gpuhash_index_create and the bench loops call it).  Idempotent, current device. */
+int gpuhash_init_device(void);
+
 /* One launch for a whole scheduler cycle of one worker (mega_scheduler.c:392-502): all searches, then all deletes,
  * then all inserts, ordered inside the kernel.  Inserts are either a flat batch (ielem_d, n_insert) or segments with
  * device-side counts (blk_input_d, blk_elem_num_d, num_blks; then ielem_d = NULL, n_insert = 0).  Any part may be empty. */

@@ -68,6 +68,7 @@ SYMBOLS = {
     "gpuhash_insert_ex": (_i, [_gp, _vp, _vp, _vp, _i, _vp, _u, _vp]),
     "gpuhash_insert_flat_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
     "gpuhash_delete_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "gpuhash_init_device": (_i, []),
     "gpuhash_cycle_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _vp, _vp]),
     "gpuhash_device_count": (_i, []),
     "gpuhash_set_device": (_i, [_i]),

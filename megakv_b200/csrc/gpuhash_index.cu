@@ -67,6 +67,7 @@ extern "C" gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo
 		size_t max_search, size_t max_insert, size_t max_delete)
 {
 	if (workers < 1 || workers > MAX_WORKERS || layout > GPUHASH_LAYOUT_REFERENCE) return NULL;
+	if (gpuhash_init_device() != 0) return NULL;
 	gpuhash_index_t *ix = (gpuhash_index_t *)calloc(1, sizeof *ix);
 	if (!ix) return NULL;
 	if (gpuhash_geom_init(&ix->geom, mem_p, algo) != 0) { free(ix); return NULL; }
@@ -233,6 +234,7 @@ extern "C" int gpuhash_bench_resident(const gpuhash_geom_t *g, void *table_d,
 		int steps, int streams, int use_graph, gpuhash_bench_result_t *res)
 {
 	if (!g || !res || steps < 1 || streams < 1 || streams > MAX_WORKERS) return -1;
+	if (gpuhash_init_device() != 0) return -1;
 	memset(res, 0, sizeof *res);
 	cudaStream_t st[MAX_WORKERS], main_s;
 	cudaEvent_t ev_start, ev_stop, ev_done[MAX_WORKERS];

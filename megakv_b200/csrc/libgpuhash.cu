@@ -273,6 +273,22 @@ extern "C" int gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, uns
 static unsigned int *g_cycle_counters[64];        /* per device: GH_CYCLE_SLOTS x 4 words, zero */
 static unsigned int g_cycle_next[64];
 
+/* Per-device state of the library (the counter slots of gpuhash_cycle_ex, cached device attributes).  Idempotent. */
+extern "C" int gpuhash_init_device(void)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+	(void)sm_count_now(); (void)l2_bytes_now();
+	if (!g_cycle_counters[dev]) {
+		unsigned int *p = NULL;
+		cudaError_t e = cudaMalloc((void **)&p, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int));
+		if (e != cudaSuccess) return (int)e;
+		if ((e = cudaMemset(p, 0, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
+		g_cycle_counters[dev] = p;
+	}
+	return 0;
+}
+
 extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
 		const void *selem_d, size_t n_search, void *out_d,
 		const void *delem_d, size_t n_delete,
@@ -285,10 +301,9 @@ extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
 	if (blk_input_d && (!blk_elem_num_d || num_blks < 1 || n_insert)) return -1;
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-	if (!g_cycle_counters[dev]) {
-		cudaError_t e = cudaMalloc((void **)&g_cycle_counters[dev], GH_CYCLE_SLOTS * 4 * sizeof(unsigned int));
-		if (e != cudaSuccess) return (int)e;
-		if ((e = cudaMemset(g_cycle_counters[dev], 0, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
+	if (!g_cycle_counters[dev]) {                    /* first use on this device (not allowed while a stream is capturing: */
+		int rc = gpuhash_init_device();              /*  gpuhash_index_create and the bench loops call this up front)      */
+		if (rc) return rc;
 	}
 	gh::CycleArgs a;
 	a.search_in = (const uint2 *)selem_d; a.search_out = (uint2 *)out_d; a.n_search = n_search;
