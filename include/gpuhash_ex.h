@@ -189,6 +189,22 @@ int gpuhash_route_gather(const void *const *staged_ptrs, const uint32_t *perm_d,
 		size_t cap, int log2_shards, void *out_d, size_t n, const uint32_t *flags_d, uint32_t wait_seq, uint32_t *err_d, void *stream);
 int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, int num_seg, const void *const *seg_in_ptrs,
 		const uint32_t *seg_count_d, size_t max_total, gpuhash_stats_t *stats_d, void *stream);
+/* The same protocol with publication and waiting folded into the producing / consuming kernels (3 launches per routed
+ * search, 2 per routed insert/delete):
+ *   route_scatter_pub  waits until ack_flags_d[0..G) >= seq-1 (owners consumed the previous batch), scatters into dst_ptrs,
+ *                      then the last CTA stores counts2_d[seq&1][d] to owner d's count cell and raises its flag to seq.
+ *                      counts2_d = uint32[2][8], zero at first use; ticket_d = one zeroed uint32 per lane.
+ *   serve              waits until req_flags_d[0..G) >= seq, then op 0: looks up the G regions and stores results to
+ *                      seg_out_ptrs (the origins' staging regions); op 1 / 2: inserts / deletes them; the last CTA raises
+ *                      the result flag (= consumption ack) to seq on every origin.
+ *   route_gather       (above, with wait_seq = seq) brings the results into request order. */
+int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
+		const void *const *dst_ptrs, uint32_t *counts2_d, uint32_t *perm_d, size_t cap, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq,
+		const uint32_t *ack_flags_d, uint32_t *err_d, void *stream);
+int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int log2_shards, const void *const *seg_in_ptrs,
+		const uint32_t *seg_count_d, const void *const *seg_out_ptrs, size_t max_total, const uint32_t *req_flags_d, uint32_t *err_d,
+		int my_rank, const void *const *peer_res_flag_ptrs, uint32_t *ticket_d, uint32_t seq, gpuhash_stats_t *stats_d, void *stream);
 /* fused path: block the stream until flags_d[0..num) >= want (peers raise them with release semantics); 2 s timeout -> *err_d = 1 */
 int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t want, uint32_t *err_d, void *stream);
 int   gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B);      /* cudaIpcGetMemHandle */

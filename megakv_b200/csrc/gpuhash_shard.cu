@@ -196,6 +196,130 @@ __global__ void wait_flags_kernel(const uint32_t *flags, int G, uint32_t want, u
 	if (threadIdx.x < G) wait_flag(flags + threadIdx.x, want, 2000000000ULL, err);
 }
 
+/* ================= fused variants: 3 launches per routed search, 2 per routed insert/delete =================
+ * Launch count, not bytes, is what a 64 K-request batch pays for (a graph kernel node costs ~1 us of front-end
+ * time on B200), so publication and waiting are folded into the kernels that produce / consume the data:
+ *   scatter+publish   every CTA first waits until the owners have consumed this rank's previous batch
+ *                     (res_flag >= seq-1), scatters, and the LAST CTA to finish (ticket) publishes counts + flag
+ *   serve             waits for all sources' flags, looks up / inserts / deletes what arrived, last CTA raises the
+ *                     result flags on every origin
+ *   gather            (searches) waits for the result flags, un-permutes                                        */
+
+struct PubArgs {
+	Ptrs peer_count, peer_flag;      /* [G] -> uint32[G] on each peer */
+	uint32_t *ticket;                /* local, zero between launches */
+	int my_rank;
+	uint32_t seq;
+};
+
+__device__ __forceinline__ bool last_cta_done(uint32_t *ticket)
+{
+	__shared__ int last;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();                                          /* this CTA's peer stores before the ticket */
+		last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	return last != 0;
+}
+
+template <int kWords>
+__global__ void __launch_bounds__(256)
+route_scatter_pub_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t hash_mask_total, int shift, int G,
+		Ptrs dst, uint32_t *counts2 /* [2][8] */, uint32_t *perm, size_t cap, PubArgs pub,
+		const uint32_t *ack_flags, uint32_t *err)
+{
+	__shared__ uint32_t blk_count[kMaxShards], blk_base[kMaxShards];
+	__shared__ int ok;
+	uint32_t *counts = counts2 + 8 * (pub.seq & 1u);
+	if (threadIdx.x == 0) {
+		ok = 1;
+		for (int s = 0; s < G && ok; s++) ok = wait_flag(ack_flags + s, pub.seq - 1u, 2000000000ULL, err);
+	}
+	__syncthreads();
+	if (ok) {
+		for (size_t tile = (size_t)blockIdx.x * blockDim.x; tile < n; tile += (size_t)gridDim.x * blockDim.x) {
+			if (threadIdx.x < kMaxShards) blk_count[threadIdx.x] = 0;
+			__syncthreads();
+			const size_t i = tile + threadIdx.x;
+			uint32_t w[kWords]; uint32_t d = 0, rank = 0;
+			if (i < n) {
+#pragma unroll
+				for (int k = 0; k < kWords; k++) w[k] = gh::ld_stream_u32(in + kWords * i + k);
+				d = (w[1] & hash_mask_total) >> shift;
+				rank = atomicAdd(&blk_count[d], 1u);
+			}
+			__syncthreads();
+			if (threadIdx.x < G && blk_count[threadIdx.x])
+				blk_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], blk_count[threadIdx.x]);
+			__syncthreads();
+			if (i < n) {
+				const size_t slot = (size_t)blk_base[d] + rank;
+				uint32_t *q = (uint32_t *)dst.p[d] + kWords * slot;
+#pragma unroll
+				for (int k = 0; k < kWords; k++) q[k] = w[k];
+				if (perm) perm[(size_t)d * cap + slot] = (uint32_t)i;
+			}
+			__syncthreads();
+		}
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G) {
+			const int d = threadIdx.x;
+			const uint32_t c = ((volatile uint32_t *)counts)[d];
+			((volatile uint32_t *)pub.peer_count.p[d])[pub.my_rank] = c;
+			__threadfence_system();
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[d] + pub.my_rank), "r"(pub.seq) : "memory");
+		}
+		if (threadIdx.x < kMaxShards) counts2[8 * ((pub.seq + 1u) & 1u) + threadIdx.x] = 0;   /* next batch's counters */
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
+template <bool kPairs, int kOp /* 0 search, 1 insert, 2 delete */>
+__global__ void __launch_bounds__(256)
+serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, Ptrs seg_out,
+		const uint32_t *req_flags, uint32_t *err, PubArgs pub, gh::Stats *st)
+{
+	__shared__ uint32_t prefix[kMaxShards + 1];
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = 1;
+		for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
+		prefix[G] = acc;
+	}
+	__syncthreads();
+	if (ok) {
+		const uint32_t total = prefix[G];
+		int s = 0;
+		for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+			while (e >= prefix[s + 1]) s++;
+			const uint32_t j = e - prefix[s];
+			if (kOp == 0) {
+				const uint2 q = ld_u2_sys((const uint2 *)seg_in.p[s] + j);
+				((uint2 *)seg_out.p[s])[j] = gh::search_one(table, g, q);
+			} else {
+				const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)j;
+				const uint2 a = ld_u2_sys(p);
+				uint32_t loc; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(loc) : "l"(p + 2) : "memory");
+				if (kOp == 1) gh::insert_one<kPairs>(table, g, a.x, a.y, loc, st);
+				else {
+					int z = gh::delete_one<kPairs>(table, g, a.x, a.y, loc);
+					if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+				}
+			}
+		}
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G)
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[threadIdx.x] + pub.my_rank), "r"(pub.seq) : "memory");
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
 int fill_ptrs(Ptrs &P, const void *const *src, int G)
 {
 	if (G < 1 || G > kMaxShards || !src) return -1;
@@ -296,6 +420,61 @@ extern "C" int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t wan
 {
 	if (!flags_d || !err_d || num < 1 || num > kMaxShards) return -1;
 	wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_d, num, want, err_d);
+	return (int)cudaGetLastError();
+}
+
+static int fill_pub(PubArgs &P, int G, int my_rank, const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs,
+		uint32_t *ticket_d, uint32_t seq)
+{
+	if (!ticket_d || fill_ptrs(P.peer_flag, peer_flag_ptrs, G)) return -1;
+	if (peer_count_ptrs) { if (fill_ptrs(P.peer_count, peer_count_ptrs, G)) return -1; }
+	else for (int k = 0; k < kMaxShards; k++) P.peer_count.p[k] = nullptr;
+	P.ticket = ticket_d; P.my_rank = my_rank; P.seq = seq;
+	return 0;
+}
+
+extern "C" int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
+		const void *const *dst_ptrs, uint32_t *counts2_d, uint32_t *perm_d, size_t cap, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq,
+		const uint32_t *ack_flags_d, uint32_t *err_d, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs D; PubArgs P;
+	if (log2_shards < 0 || log2_shards > 3 || (elem_words != 2 && elem_words != 3) || fill_ptrs(D, dst_ptrs, G) || !counts2_d
+			|| n > cap || !ack_flags_d || !err_d || !peer_count_ptrs || fill_pub(P, G, my_rank, peer_count_ptrs, peer_flag_ptrs, ticket_d, seq)) return -1;
+	int bits = 0; while ((hash_mask_total >> bits) & 1u) bits++;
+	const int shift = bits - log2_shards;
+	if (shift < 0) return -1;
+	const unsigned blocks = grid_for(n ? n : 1, 16);
+	cudaStream_t s = (cudaStream_t)stream;
+	if (elem_words == 2)
+		route_scatter_pub_kernel<2><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+	else
+		route_scatter_pub_kernel<3><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+	return (int)cudaGetLastError();
+}
+
+/* op: 0 search (seg_out_ptrs = origins' staging regions), 1 insert, 2 delete (seg_out_ptrs = NULL) */
+extern "C" int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int log2_shards, const void *const *seg_in_ptrs,
+		const uint32_t *seg_count_d, const void *const *seg_out_ptrs, size_t max_total, const uint32_t *req_flags_d, uint32_t *err_d,
+		int my_rank, const void *const *peer_res_flag_ptrs, uint32_t *ticket_d, uint32_t seq, gpuhash_stats_t *stats_d, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs I, O; PubArgs P;
+	if (!g || op < 0 || op > 2 || fill_ptrs(I, seg_in_ptrs, G) || !seg_count_d || !req_flags_d || !err_d
+			|| fill_pub(P, G, my_rank, NULL, peer_res_flag_ptrs, ticket_d, seq)) return -1;
+	if (op == 0) { if (fill_ptrs(O, seg_out_ptrs, G)) return -1; }
+	else for (int k = 0; k < kMaxShards; k++) O.p[k] = nullptr;
+	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo; gg.layout = g->layout;
+	const unsigned blocks = grid_for(max_total ? max_total : 1, 8);
+	cudaStream_t s = (cudaStream_t)stream;
+	gh::Bucket *t = (gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
+	const bool pairs = gg.layout == gh::kLayoutPairs;
+#define GH_SERVE(P_, OP_) serve_kernel<P_, OP_><<<blocks, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P, st)
+	if (op == 0)      { if (pairs) GH_SERVE(true, 0); else GH_SERVE(false, 0); }
+	else if (op == 1) { if (pairs) GH_SERVE(true, 1); else GH_SERVE(false, 1); }
+	else              { if (pairs) GH_SERVE(true, 2); else GH_SERVE(false, 2); }
+#undef GH_SERVE
 	return (int)cudaGetLastError();
 }
 

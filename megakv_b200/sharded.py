@@ -198,7 +198,8 @@ class CudaShardBackend:
         self.off_inbox, self.off_stage = 0, G * cap * 12
         self.off_cnt = self.off_stage + G * cap * 8
         self.off_reqf, self.off_resf, self.off_err = self.off_cnt + 32, self.off_cnt + 64, self.off_cnt + 96
-        self.arena = DeviceBuffer(self.off_cnt + 128, zero=True)
+        self.off_cnt2, self.off_ticket = self.off_cnt + 128, self.off_cnt + 192     # local only: counters [2][8], tickets [2]
+        self.arena = DeviceBuffer(self.off_cnt + 256, zero=True)
         handle = (C.c_ubyte * 64)()
         N.check(L.gpuhash_ipc_export(self.arena.ptr, handle), "cudaIpcGetMemHandle")
         mine = t.tensor(list(handle), dtype=t.uint8, device=self.dev)
@@ -230,49 +231,38 @@ class CudaShardBackend:
         self.p2p = True
 
     def _p2p_scatter(self, ix, req, words, want_perm):
-        """requests -> owners' inboxes (my region of each), counts + flag published to every owner"""
-        L, N, st = self.L, self.N, self._stream()
-        n = req.shape[0]
+        """one launch: wait for the owners' ack of my previous batch, scatter into their inboxes, publish counts + flag"""
+        L, N, A = self.L, self.N, self.arena.ptr
         ix.seq += 1
-        N.check(L.gpuhash_route_scatter(req.data_ptr(), n, words, self.plan.hash_mask_total, self.plan.log2,
-                                        self.pp_peer_inbox, self.counts.data_ptr(),
-                                        self.perm.data_ptr() if want_perm else None, self.cap, st), "gpuhash_route_scatter")
-        N.check(L.gpuhash_route_publish(self.counts.data_ptr(), self.plan.log2, self.rank, self.pp_peer_cnt,
-                                        self.pp_peer_reqf, ix.seq, st), "gpuhash_route_publish")
-        # everything enqueued after this sees what all sources published for batch ix.seq
-        N.check(L.gpuhash_wait_flags(self.arena.ptr + self.off_reqf, self.G, ix.seq, self.arena.ptr + self.off_err, st),
-                "gpuhash_wait_flags")
+        N.check(L.gpuhash_route_scatter_pub(req.data_ptr() if req.shape[0] else None, req.shape[0], words,
+                                            self.plan.hash_mask_total, self.plan.log2, self.pp_peer_inbox, A + self.off_cnt2,
+                                            self.perm.data_ptr() if want_perm else None, self.cap, self.rank,
+                                            self.pp_peer_cnt, self.pp_peer_reqf, A + self.off_ticket, ix.seq,
+                                            A + self.off_resf, A + self.off_err, self._stream()), "gpuhash_route_scatter_pub")
+
+    def _p2p_serve(self, ix, op):
+        L, N, A = self.L, self.N, self.arena.ptr
+        N.check(L.gpuhash_serve(C.byref(self.geom), self.table.ptr, op, self.plan.log2, self.pp_my_inbox, A + self.off_cnt,
+                                self.pp_origin_stage if op == 0 else None, self.G * self.cap, A + self.off_reqf, A + self.off_err,
+                                self.rank, self.pp_peer_resf, A + self.off_ticket + 4, ix.seq, None, self._stream()), "gpuhash_serve")
 
     def p2p_search(self, ix, sel, out=None):
-        L, N, st = self.L, self.N, self._stream()
+        """3 launches: scatter+publish, serve (lookup + result flags), gather"""
+        L, N, A = self.L, self.N, self.arena.ptr
         n = sel.shape[0]
         self._p2p_scatter(ix, sel, 2, True)
-        N.check(L.gpuhash_search_segments(C.byref(self.geom), self.table.ptr, self.G, self.pp_my_inbox,
-                                          self.arena.ptr + self.off_cnt, self.pp_origin_stage, self.G * self.cap,
-                                          None, 0, None, st), "gpuhash_search_segments")
-        N.check(L.gpuhash_results_publish(self.plan.log2, self.rank, self.pp_peer_resf, ix.seq, st), "gpuhash_results_publish")
+        self._p2p_serve(ix, 0)
         if out is None:
             out = self.empty(n, 2)
-        N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), self.counts.data_ptr(), self.cap,
-                                       self.plan.log2, out.data_ptr() if n else None, n, self.arena.ptr + self.off_resf, ix.seq,
-                                       self.arena.ptr + self.off_err, st), "gpuhash_route_gather")
+        N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), A + self.off_cnt2 + 32 * (ix.seq & 1), self.cap,
+                                       self.plan.log2, out.data_ptr() if n else None, n, A + self.off_resf, ix.seq,
+                                       A + self.off_err, self._stream()), "gpuhash_route_gather")
         return out
 
     def p2p_update(self, ix, iel, insert):
-        L, N, st = self.L, self.N, self._stream()
+        """2 launches: scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter."""
         self._p2p_scatter(ix, iel, 3, False)
-        if insert:
-            N.check(L.gpuhash_insert_ex(C.byref(self.geom), self.table.ptr, self.seg_ptrs_d.data_ptr(),
-                                        self.arena.ptr + self.off_cnt, self.G, None, 0, st), "gpuhash_insert_ex")
-        else:
-            N.check(L.gpuhash_delete_segments(C.byref(self.geom), self.table.ptr, self.G, self.pp_my_inbox,
-                                              self.arena.ptr + self.off_cnt, self.G * self.cap, None, st),
-                    "gpuhash_delete_segments")
-        # the inbox may be overwritten by the sources' next batch only after this rank has consumed it: raise the
-        # result flags too, and make the sources wait on them before they go on
-        N.check(L.gpuhash_results_publish(self.plan.log2, self.rank, self.pp_peer_resf, ix.seq, st), "gpuhash_results_publish")
-        N.check(L.gpuhash_wait_flags(self.arena.ptr + self.off_resf, self.G, ix.seq, self.arena.ptr + self.off_err, st),
-                "gpuhash_wait_flags")
+        self._p2p_serve(ix, 1 if insert else 2)
 
     def p2p_error(self):
         """1 if a flag wait timed out (a peer died); checked by the callers after synchronising"""

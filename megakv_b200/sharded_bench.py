@@ -47,7 +47,7 @@ def main(args, rank, world, local_rank, log):
     ixc = ShardedIndex(be, plan, exchange="collective")          # same table, NCCL exchange (baseline)
     # S lanes = S batches in flight per GPU, each with its own inboxes/staging/flags and stream (the sharded
     # counterpart of the reference's one-stream-per-worker, mega_scheduler.c:276-280)
-    S = max(1, min(args.streams, 16))
+    S = max(1, min(args.streams, 32))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
@@ -185,7 +185,7 @@ def main(args, rank, world, local_rank, log):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
                     "d2h_bytes_per_step": 8 * N_SEARCH, "steps": e_steps},
-            "gpu_launches": steps * 12,
+            "gpu_launches": steps * 5,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": None, "kernel": "search_segments_kernel (per GPU, routed)", "peak_source": peak_src,
                          "note": "search path only, includes both NVLink exchanges"},
