@@ -303,8 +303,10 @@ serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *
 				((uint2 *)seg_out.p[s])[j] = gh::search_one(table, g, q);
 			} else {
 				const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)j;
-				const uint2 a = ld_u2_sys(p);
-				uint32_t loc; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(loc) : "l"(p + 2) : "memory");
+				uint2 a; uint32_t loc;                                   /* 12-byte records: scalar loads */
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a.x) : "l"(p) : "memory");
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a.y) : "l"(p + 1) : "memory");
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(loc) : "l"(p + 2) : "memory");
 				if (kOp == 1) gh::insert_one<kPairs>(table, g, a.x, a.y, loc, st);
 				else {
 					int z = gh::delete_one<kPairs>(table, g, a.x, a.y, loc);
