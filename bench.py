@@ -19,6 +19,8 @@ order, mega_scheduler.c:392-502); batches go round-robin over S streams like the
   --impl reference : the reference's algorithm on the host cores (oracle, all threads) -- same metric/config.
 """
 import argparse
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream/lane (before CUDA starts)
 import ctypes as C
 import json
 import os

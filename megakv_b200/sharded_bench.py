@@ -109,6 +109,29 @@ def main(args, rank, world, local_rank, log):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    def phase_profile(count=200):
+        """one lane, call by call, CUDA events around every launch: where a routed step spends its time (us, this rank)"""
+        lane, be_l = lanes[0], lanes[0].be
+        names = ["search.scatter+publish", "search.serve", "search.gather", "insert.scatter+publish", "insert.serve"]
+        acc = [0.0] * 5
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        A = be_l.arena.ptr
+        for i in range(count):
+            b = i % kd
+            torch.cuda.synchronize(); dist.barrier()
+            ev[0].record()
+            be_l._p2p_scatter(lane, sel[b], 2, True); ev[1].record()
+            be_l._p2p_serve(lane, 0); ev[2].record()
+            N.check(L.gpuhash_route_gather(be_l.pp_my_stage, be_l.perm.data_ptr(), A + be_l.off_cnt2 + 32 * (lane.seq & 1), be_l.cap,
+                                           plan.log2, out[b].data_ptr(), N_SEARCH, A + be_l.off_resf, lane.seq, A + be_l.off_err,
+                                           be_l._stream())); ev[3].record()
+            be_l._p2p_scatter(lane, ins[b], 3, False); ev[4].record()
+            be_l._p2p_serve(lane, 1); ev[5].record()
+            torch.cuda.synchronize()
+            for k in range(5):
+                acc[k] += ev[k].elapsed_time(ev[k + 1]) * 1e3
+        return {n: round(a / count, 2) for n, a in zip(names, acc)}
+
     use_graph = bool(args.graph)
     try:
         timed(None, 0, warm, use_graph)                                 # warm-up
@@ -128,6 +151,7 @@ def main(args, rank, world, local_rank, log):
 
     with sampler:
         t_s = timed(None, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
+    phases = phase_profile()
     # NCCL baseline on fewer steps (host sync per exchange)
     kb = min(steps, 200)
     timed(ixc, 0, 3, False)
@@ -150,8 +174,9 @@ def main(args, rank, world, local_rank, log):
         cur = torch.cuda.current_stream()
         for st in streams:
             st.wait_stream(cur)
+        Se = min(S, 8)              # call-by-call launches: at most as many lanes as hardware queues
         for i in range(count):
-            k, b = i % S, i % ke
+            k, b = i % Se, i % ke
             with torch.cuda.stream(streams[k]):
                 ds[k].copy_(hs[b], non_blocking=True); di[k].copy_(hi[b], non_blocking=True)
                 lanes[k].search(ds[k], do[k]); lanes[k].insert(di[k])
@@ -191,6 +216,7 @@ def main(args, rank, world, local_rank, log):
                          "note": "search path only, includes both NVLink exchanges"},
             "nccl_baseline": {"value": round(world * kb * BATCH / t_nccl / 1e6, 1), "unit": "Mops/s", "steps": kb,
                               "what": "same steps, exchanges through torch.distributed all_to_all_single"},
+            "phase_us_one_lane": phases,
             "cpu_baseline": None, "clocks": sampler.summary(), "search_hit_fraction": round(hit, 5),
         }
         print(json.dumps(line), flush=True)
