@@ -197,7 +197,11 @@ int gpuhash_delete_segments(const gpuhash_geom_t *g, void *table_d, int num_seg,
  *   serve              waits until req_flags_d[0..G) >= seq, then op 0: looks up the G regions and stores results to
  *                      seg_out_ptrs (the origins' staging regions); op 1 / 2: inserts / deletes them; the last CTA raises
  *                      the result flag (= consumption ack) to seq on every origin.
- *   route_gather       (above, with wait_seq = seq) brings the results into request order. */
+ *   route_gather       (above, with wait_seq = seq) brings the results into request order.
+ * ack_flags_d / req_flags_d may be NULL: then the kernel does not wait and the caller orders the stream with
+ * gpuhash_wait_flags (one tiny CTA) instead.  That is what megakv_b200/sharded.py does: a waiting CTA inside a large
+ * kernel keeps an SM slot, and with many batches in flight the GPUs can fill up with CTAs waiting for each other's
+ * producers -- a distributed deadlock that only the 2 s timeout breaks (seen at 32 lanes on 2 GPUs). */
 int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
 		const void *const *dst_ptrs, uint32_t *counts2_d, uint32_t *perm_d, size_t cap, int my_rank,
 		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq,

@@ -235,7 +235,7 @@ route_scatter_pub_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t has
 	uint32_t *counts = counts2 + 8 * (pub.seq & 1u);
 	if (threadIdx.x == 0) {
 		ok = 1;
-		for (int s = 0; s < G && ok; s++) ok = wait_flag(ack_flags + s, pub.seq - 1u, 2000000000ULL, err);
+		if (ack_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(ack_flags + s, pub.seq - 1u, 2000000000ULL, err);
 	}
 	__syncthreads();
 	if (ok) {
@@ -286,7 +286,7 @@ serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *
 	__shared__ int ok;
 	if (threadIdx.x == 0) {
 		ok = 1;
-		for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
+		if (req_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
 		uint32_t acc = 0;
 		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
 		prefix[G] = acc;
@@ -435,7 +435,7 @@ serve_search_quad_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G
 	__shared__ int ok;
 	if (threadIdx.x == 0) {
 		ok = 1;
-		for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
+		if (req_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
 		uint32_t acc = 0;
 		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
 		prefix[G] = acc;
@@ -512,7 +512,7 @@ extern "C" int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_wo
 	const int G = 1 << log2_shards;
 	Ptrs D; PubArgs P;
 	if (log2_shards < 0 || log2_shards > 3 || (elem_words != 2 && elem_words != 3) || fill_ptrs(D, dst_ptrs, G) || !counts2_d
-			|| n > cap || !ack_flags_d || !err_d || !peer_count_ptrs || fill_pub(P, G, my_rank, peer_count_ptrs, peer_flag_ptrs, ticket_d, seq)) return -1;
+			|| n > cap || (ack_flags_d && !err_d) || !peer_count_ptrs || fill_pub(P, G, my_rank, peer_count_ptrs, peer_flag_ptrs, ticket_d, seq)) return -1;
 	int bits = 0; while ((hash_mask_total >> bits) & 1u) bits++;
 	const int shift = bits - log2_shards;
 	if (shift < 0) return -1;
@@ -532,7 +532,7 @@ extern "C" int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int
 {
 	const int G = 1 << log2_shards;
 	Ptrs I, O; PubArgs P;
-	if (!g || op < 0 || op > 2 || fill_ptrs(I, seg_in_ptrs, G) || !seg_count_d || !req_flags_d || !err_d
+	if (!g || op < 0 || op > 2 || fill_ptrs(I, seg_in_ptrs, G) || !seg_count_d || (req_flags_d && !err_d)
 			|| fill_pub(P, G, my_rank, NULL, peer_res_flag_ptrs, ticket_d, seq)) return -1;
 	if (op == 0) { if (fill_ptrs(O, seg_out_ptrs, G)) return -1; }
 	else for (int k = 0; k < kMaxShards; k++) O.p[k] = nullptr;

@@ -230,39 +230,49 @@ class CudaShardBackend:
         t.cuda.synchronize()
         self.p2p = True
 
+    # Waits are separate one-CTA launches (gpuhash_wait_flags): a CTA that waits inside a big kernel keeps an SM slot,
+    # and with many lanes in flight two GPUs can fill up with CTAs waiting for each other's producers.
+    def _wait(self, off, seq):
+        A = self.arena.ptr
+        self.N.check(self.L.gpuhash_wait_flags(A + off, self.G, seq, A + self.off_err, self._stream()), "gpuhash_wait_flags")
+
     def _p2p_scatter(self, ix, req, words, want_perm):
-        """one launch: wait for the owners' ack of my previous batch, scatter into their inboxes, publish counts + flag"""
+        """wait for the owners' ack of my previous batch; scatter into their inboxes; last CTA publishes counts + flag"""
         L, N, A = self.L, self.N, self.arena.ptr
         ix.seq += 1
+        if ix.seq > 1:
+            self._wait(self.off_resf, ix.seq - 1)
         N.check(L.gpuhash_route_scatter_pub(req.data_ptr() if req.shape[0] else None, req.shape[0], words,
                                             self.plan.hash_mask_total, self.plan.log2, self.pp_peer_inbox, A + self.off_cnt2,
                                             self.perm.data_ptr() if want_perm else None, self.cap, self.rank,
                                             self.pp_peer_cnt, self.pp_peer_reqf, A + self.off_ticket, ix.seq,
-                                            A + self.off_resf, A + self.off_err, self._stream()), "gpuhash_route_scatter_pub")
+                                            None, None, self._stream()), "gpuhash_route_scatter_pub")
 
-    def _p2p_serve(self, ix, op):
+    def _p2p_serve(self, ix, op, n_hint=0):
         L, N, A = self.L, self.N, self.arena.ptr
+        self._wait(self.off_reqf, ix.seq)
         N.check(L.gpuhash_serve(C.byref(self.geom), self.table.ptr, op, self.plan.log2, self.pp_my_inbox, A + self.off_cnt,
-                                self.pp_origin_stage if op == 0 else None, self.G * self.cap, A + self.off_reqf, A + self.off_err,
+                                self.pp_origin_stage if op == 0 else None, n_hint or self.G * self.cap, None, None,
                                 self.rank, self.pp_peer_resf, A + self.off_ticket + 4, ix.seq, None, self._stream()), "gpuhash_serve")
 
     def p2p_search(self, ix, sel, out=None):
-        """3 launches: scatter+publish, serve (lookup + result flags), gather"""
+        """scatter+publish, serve (lookup + result flags), gather -- each behind a one-CTA flag wait"""
         L, N, A = self.L, self.N, self.arena.ptr
         n = sel.shape[0]
         self._p2p_scatter(ix, sel, 2, True)
-        self._p2p_serve(ix, 0)
+        self._p2p_serve(ix, 0, 2 * max(n, 1))           # uniform keys: about n requests arrive; the grid strides if more do
         if out is None:
             out = self.empty(n, 2)
+        self._wait(self.off_resf, ix.seq)
         N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), A + self.off_cnt2 + 32 * (ix.seq & 1), self.cap,
-                                       self.plan.log2, out.data_ptr() if n else None, n, A + self.off_resf, ix.seq,
-                                       A + self.off_err, self._stream()), "gpuhash_route_gather")
+                                       self.plan.log2, out.data_ptr() if n else None, n, None, 0, None, self._stream()),
+                "gpuhash_route_gather")
         return out
 
     def p2p_update(self, ix, iel, insert):
-        """2 launches: scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter."""
+        """scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter."""
         self._p2p_scatter(ix, iel, 3, False)
-        self._p2p_serve(ix, 1 if insert else 2)
+        self._p2p_serve(ix, 1 if insert else 2, 2 * max(iel.shape[0], 1))
 
     def p2p_error(self):
         """1 if a flag wait timed out (a peer died); checked by the callers after synchronising"""

@@ -122,9 +122,9 @@ def main(args, rank, world, local_rank, log):
             ev[0].record()
             be_l._p2p_scatter(lane, sel[b], 2, True); ev[1].record()
             be_l._p2p_serve(lane, 0); ev[2].record()
+            be_l._wait(be_l.off_resf, lane.seq)
             N.check(L.gpuhash_route_gather(be_l.pp_my_stage, be_l.perm.data_ptr(), A + be_l.off_cnt2 + 32 * (lane.seq & 1), be_l.cap,
-                                           plan.log2, out[b].data_ptr(), N_SEARCH, A + be_l.off_resf, lane.seq, A + be_l.off_err,
-                                           be_l._stream())); ev[3].record()
+                                           plan.log2, out[b].data_ptr(), N_SEARCH, None, 0, None, be_l._stream())); ev[3].record()
             be_l._p2p_scatter(lane, ins[b], 3, False); ev[4].record()
             be_l._p2p_serve(lane, 1); ev[5].record()
             torch.cuda.synchronize()
@@ -210,7 +210,7 @@ def main(args, rank, world, local_rank, log):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
                     "d2h_bytes_per_step": 8 * N_SEARCH, "steps": e_steps},
-            "gpu_launches": steps * 5,
+            "gpu_launches": steps * 10,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": None, "kernel": "search_segments_kernel (per GPU, routed)", "peak_source": peak_src,
                          "note": "search path only, includes both NVLink exchanges"},
