@@ -49,14 +49,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns()
  * *err so that a dead peer turns into an error code, not a hung box. */
 __device__ __forceinline__ bool wait_flag(const volatile uint32_t *flag, uint32_t want, uint64_t timeout_ns, uint32_t *err)
 {
+	/* poll with relaxed loads (an acquire at system scope invalidates this SM's L1 every time it is issued, which
+	 * the kernels running next to the waiter pay for), then ONE acquire fence once the flag is there */
 	uint64_t t0 = globaltimer_ns();
 	for (;;) {
 		uint32_t v;
-		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-		if ((int32_t)(v - want) >= 0) return true;
+		asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if ((int32_t)(v - want) >= 0) break;
 		if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1u); return false; }
-		__nanosleep(200);
+		__nanosleep(256);
 	}
+	asm volatile("fence.acq_rel.sys;" ::: "memory");
+	return true;
 }
 
 /* ---- K1: scatter a batch into per-owner regions ------------------------------------------------- */

@@ -47,7 +47,8 @@ def main(args, rank, world, local_rank, log):
     ixc = ShardedIndex(be, plan, exchange="collective")          # same table, NCCL exchange (baseline)
     # S lanes = S batches in flight per GPU, each with its own inboxes/staging/flags and stream (the sharded
     # counterpart of the reference's one-stream-per-worker, mega_scheduler.c:276-280)
-    S = max(1, min(args.streams, 32))
+    S = max(1, min(int(os.environ.get('GPUHASH_LANES', args.streams)), 64))
+    quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
@@ -149,6 +150,12 @@ def main(args, rank, world, local_rank, log):
     hit = float(((chk[:, 0] != 0) | (chk[:, 1] != 0)).mean())
     assert hit > 0.999, f"searches did not hit: {hit}"
 
+    if quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "graph": use_graph, "value_Mops": round(value, 1),
+                              "us_per_step": round(t_val / steps * 1e6, 2)}), flush=True)
+        dist.barrier(); dist.destroy_process_group()
+        return 0
     with sampler:
         t_s = timed(None, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
     phases = phase_profile()
