@@ -209,8 +209,11 @@ int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_words, uint32
 int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int log2_shards, const void *const *seg_in_ptrs,
 		const uint32_t *seg_count_d, const void *const *seg_out_ptrs, size_t max_total, const uint32_t *req_flags_d, uint32_t *err_d,
 		int my_rank, const void *const *peer_res_flag_ptrs, uint32_t *ticket_d, uint32_t seq, gpuhash_stats_t *stats_d, void *stream);
-/* fused path: block the stream until flags_d[0..num) >= want (peers raise them with release semantics); 2 s timeout -> *err_d = 1 */
+/* fused path: block the stream until flags_d[0..num) >= want (peers raise them with release semantics).  Done with stream
+ * memory operations (no SM, graph-capturable) when the driver offers them (gpuhash_wait_mode() == 1), else by a one-CTA
+ * kernel with a 2 s timeout (-> *err_d = 1).  GPUHASH_WAIT_MODE=kernel forces the latter. */
 int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t want, uint32_t *err_d, void *stream);
+int gpuhash_wait_mode(void);
 int   gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B);      /* cudaIpcGetMemHandle */
 void *gpuhash_ipc_import(const void *handle_64B);                   /* cudaIpcOpenMemHandle, NULL on failure */
 int   gpuhash_ipc_close(void *imported_ptr);

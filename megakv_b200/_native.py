@@ -116,6 +116,7 @@ SYMBOLS = {
     "gpuhash_route_scatter_pub": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "gpuhash_serve": (_i, [_gp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _i, _vp, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_wait_flags": (_i, [_vp, _i, C.c_uint32, _vp, _vp]),
+    "gpuhash_wait_mode": (_i, []),
     "gpuhash_ipc_export": (_i, [_vp, _vp]),
     "gpuhash_ipc_import": (_vp, [_vp]),
     "gpuhash_ipc_close": (_i, [_vp]),

@@ -152,7 +152,7 @@ def main(args, rank, world, local_rank, log):
 
     if quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "graph": use_graph, "value_Mops": round(value, 1),
+            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
                               "us_per_step": round(t_val / steps * 1e6, 2)}), flush=True)
         dist.barrier(); dist.destroy_process_group()
         return 0
