@@ -469,6 +469,75 @@ extern "C" int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t wan
 }
 extern "C" int gpuhash_wait_mode(void) { if (g_wait_mode < 0) resolve_wait_mode(); return g_wait_mode; }
 
+/* serve, op 0, four lanes per request: each bucket of a routed request is ONE L2 request (see search_quad_kernel) */
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+serve_search_quad_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, Ptrs seg_out,
+		const uint32_t *req_flags, uint32_t *err, PubArgs pub)
+{
+	__shared__ uint32_t prefix[kMaxShards + 1];
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = 1;
+		if (req_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
+		prefix[G] = acc;
+	}
+	__syncthreads();
+	if (ok) {
+		const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
+		const uint32_t total = prefix[G], total_up = (total + 7u) & ~7u;
+		const uint32_t per_iter = (gridDim.x * blockDim.x) >> 2;
+		int s = 0;
+		for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; e < total_up; e += per_iter) {
+			const bool live = e < total;
+			uint2 q = make_uint2(0u, 0u);
+			gh::Row r;
+#pragma unroll
+			for (int k = 0; k < 8; k++) r.w[k] = 0;
+			uint32_t j = 0;
+			if (live) {
+				while (e >= prefix[s + 1]) s++;
+				j = e - prefix[s];
+				q = ld_u2_sys((const uint2 *)seg_in.p[s] + j);
+				const uint32_t b = sub < 2 ? gh::bucket1(g, q.y) : gh::bucket2(g, q.y, q.x);
+				r = gh::ld_row_ro(table[b].w + 8 * half);
+			}
+			uint2 o;
+			if (kPairs) {
+				uint32_t m = (r.w[0] == q.x ? 1u : 0u) | (r.w[2] == q.x ? 2u : 0u) | (r.w[4] == q.x ? 4u : 0u) | (r.w[6] == q.x ? 8u : 0u);
+				const uint32_t loc = (m & 1u) ? r.w[1] : (m & 2u) ? r.w[3] : (m & 4u) ? r.w[5] : r.w[7];
+				if (!live) m = 0;
+				const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));
+				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
+				o = make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u);
+			} else {
+				const uint32_t m = live ? gh::eq_mask(r, q.x) : 0u;
+				const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));
+				const int l = __ffs(msig | 0x100u) - 1 & 7;
+				uint32_t loc = r.w[0];
+				if (l == 1) loc = r.w[1];
+				if (l == 2) loc = r.w[2];
+				if (l == 3) loc = r.w[3];
+				if (l == 4) loc = r.w[4];
+				if (l == 5) loc = r.w[5];
+				if (l == 6) loc = r.w[6];
+				if (l == 7) loc = r.w[7];
+				if (!msig) loc = 0;
+				o = make_uint2(__shfl_sync(0xffffffffu, loc, grp0 + 1), __shfl_sync(0xffffffffu, loc, grp0 + 3));
+			}
+			if (live && sub == 0) ((uint2 *)seg_out.p[s])[j] = o;
+		}
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G)
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[threadIdx.x] + pub.my_rank), "r"(pub.seq) : "memory");
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
 static int fill_pub(PubArgs &P, int G, int my_rank, const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs,
 		uint32_t *ticket_d, uint32_t seq)
 {
