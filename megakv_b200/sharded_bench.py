@@ -47,9 +47,14 @@ def main(args, rank, world, local_rank, log):
     ixc = ShardedIndex(be, plan, exchange="collective")          # same table, NCCL exchange (baseline)
     # S lanes = S batches in flight per GPU, each with its own inboxes/staging/flags and stream (the sharded
     # counterpart of the reference's one-stream-per-worker, mega_scheduler.c:276-280)
-    S = max(1, min(int(os.environ.get('GPUHASH_LANES', args.streams)), 64))
+    # One exchange routes GROUP consecutive 64 K batches of this GPU at once -- what the reference's scheduler cycle does
+    # with the batches of all its workers (mega_scheduler.c:392-502 loops over cpu_worker_num <= 16 buffers per cycle).
+    # A graph node costs ~2 us of front-end time here and a routed batch needs ten of them, so per-batch exchanges are
+    # node-bound (2 GPUs: 22 us per 64 K batch however many lanes); per-cycle exchanges are not.
+    GROUP = max(1, int(os.environ.get('GPUHASH_GROUP', 16)))
+    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 6)), 16))
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
-    lanes = [ShardedIndex(CudaShardBackend(plan, rank, BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
+    lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
     # ---- preload through the routed insert path: rank r inserts key indices r, r + world, ... in chunks
@@ -64,8 +69,8 @@ def main(args, rank, world, local_rank, log):
     torch.cuda.synchronize(); dist.barrier()
     log(f"preloaded {pop} keys over {world} shards in {time.time() - t0:.2f} s (p2p err={be.p2p_error()})")
 
-    # ---- resident batches
-    kd = min(steps + warm, 2048)
+    # ---- resident batches (whole cycles of GROUP batches)
+    kd = -(-min(steps + warm, 2048) // GROUP) * GROUP
     sel = torch.empty((kd, N_SEARCH, 2), dtype=torch.int32, device=dev)
     ins = torch.empty((kd, N_INSERT, 3), dtype=torch.int32, device=dev)
     out = torch.empty((kd, N_SEARCH, 2), dtype=torch.int32, device=dev)
@@ -73,23 +78,33 @@ def main(args, rank, world, local_rank, log):
     N.check(L.gpuhash_gen_inserts(ins.data_ptr(), None, SEED, pop + rank * (1 << 26), N_INSERT * kd, be._stream()))
     torch.cuda.synchronize()
 
+    sel_f, ins_f, out_f = sel.view(-1, 2), ins.view(-1, 3), out.view(-1, 2)
+
+    def cycles_of(first, count):
+        """(first batch, number of batches <= GROUP) for exactly `count` batches starting at `first`, never wrapping"""
+        i = 0
+        while i < count:
+            b = (first + i) % kd
+            g = min(GROUP, count - i, kd - b)
+            yield b, g
+            i += g
+
     def run_steps(index, first, count, with_insert=True):
+        """exactly `count` batches, up to GROUP of them per exchange"""
         if index is not None:                                           # one lane, one stream (NCCL baseline)
-            for i in range(count):
-                b = (first + i) % kd
-                index.search(sel[b], out[b])
+            for b, g in cycles_of(first, count):
+                index.search(sel_f[b * N_SEARCH:(b + g) * N_SEARCH], out_f[b * N_SEARCH:(b + g) * N_SEARCH])
                 if with_insert:
-                    index.insert(ins[b])
+                    index.insert(ins_f[b * N_INSERT:(b + g) * N_INSERT])
             return
         cur = torch.cuda.current_stream()
         for st in streams:
             st.wait_stream(cur)
-        for i in range(count):
-            b = (first + i) % kd
-            with torch.cuda.stream(streams[i % S]):
-                lanes[i % S].search(sel[b], out[b])
+        for c, (b, g) in enumerate(cycles_of(first, count)):
+            with torch.cuda.stream(streams[c % S]):
+                lanes[c % S].search(sel_f[b * N_SEARCH:(b + g) * N_SEARCH], out_f[b * N_SEARCH:(b + g) * N_SEARCH])
                 if with_insert:
-                    lanes[i % S].insert(ins[b])
+                    lanes[c % S].insert(ins_f[b * N_INSERT:(b + g) * N_INSERT])
         for st in streams:
             cur.wait_stream(st)
 
@@ -110,7 +125,7 @@ def main(args, rank, world, local_rank, log):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    def phase_profile(count=200):
+    def phase_profile(count=40):
         """one lane, call by call, CUDA events around every launch: where a routed step spends its time (us, this rank)"""
         lane, be_l = lanes[0], lanes[0].be
         names = ["search.scatter+publish", "search.serve", "search.gather", "insert.scatter+publish", "insert.serve"]
@@ -118,16 +133,17 @@ def main(args, rank, world, local_rank, log):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         A = be_l.arena.ptr
         for i in range(count):
-            b = i % kd
+            b = (i * GROUP) % kd
+            sq, iq, oq = sel_f[b * N_SEARCH:(b + GROUP) * N_SEARCH], ins_f[b * N_INSERT:(b + GROUP) * N_INSERT], out_f[b * N_SEARCH:(b + GROUP) * N_SEARCH]
             torch.cuda.synchronize(); dist.barrier()
             ev[0].record()
-            be_l._p2p_scatter(lane, sel[b], 2, True); ev[1].record()
-            be_l._p2p_serve(lane, 0); ev[2].record()
+            be_l._p2p_scatter(lane, sq, 2, True); ev[1].record()
+            be_l._p2p_serve(lane, 0, 2 * sq.shape[0]); ev[2].record()
             be_l._wait(be_l.off_resf, lane.seq)
             N.check(L.gpuhash_route_gather(be_l.pp_my_stage, be_l.perm.data_ptr(), A + be_l.off_cnt2 + 32 * (lane.seq & 1), be_l.cap,
-                                           plan.log2, out[b].data_ptr(), N_SEARCH, None, 0, None, be_l._stream())); ev[3].record()
-            be_l._p2p_scatter(lane, ins[b], 3, False); ev[4].record()
-            be_l._p2p_serve(lane, 1); ev[5].record()
+                                           plan.log2, oq.data_ptr(), oq.shape[0], None, 0, None, be_l._stream())); ev[3].record()
+            be_l._p2p_scatter(lane, iq, 3, False); ev[4].record()
+            be_l._p2p_serve(lane, 1, 2 * iq.shape[0]); ev[5].record()
             torch.cuda.synchronize()
             for k in range(5):
                 acc[k] += ev[k].elapsed_time(ev[k + 1]) * 1e3
@@ -152,7 +168,7 @@ def main(args, rank, world, local_rank, log):
 
     if quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
+            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "group": GROUP, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
                               "us_per_step": round(t_val / steps * 1e6, 2)}), flush=True)
         dist.barrier(); dist.destroy_process_group()
         return 0
@@ -160,19 +176,20 @@ def main(args, rank, world, local_rank, log):
         t_s = timed(None, warm, steps, use_graph, with_insert=False)      # search kernel path only (roofline)
     phases = phase_profile()
     # NCCL baseline on fewer steps (host sync per exchange)
-    kb = min(steps, 200)
-    timed(ixc, 0, 3, False)
+    kb = min(steps, 10 * GROUP)
+    timed(ixc, 0, GROUP, False)
     t_nccl = timed(ixc, warm, kb, False)
 
-    # e2e: pinned host -> device -> routed lookup -> pinned host, every step
-    ke = min(steps, 512)
-    hs = torch.empty((ke, N_SEARCH, 2), dtype=torch.int32).pin_memory(); hs.copy_(sel[:ke].cpu())
-    hi = torch.empty((ke, N_INSERT, 3), dtype=torch.int32).pin_memory()
+    # e2e: pinned host -> device -> routed lookup -> pinned host, every cycle of GROUP batches
+    ke = min(steps, 32 * GROUP)
+    hs = torch.empty((ke * N_SEARCH, 2), dtype=torch.int32).pin_memory(); hs.copy_(sel_f[: ke * N_SEARCH].cpu())
+    hi = torch.empty((ke * N_INSERT, 3), dtype=torch.int32).pin_memory()
     N.check(L.gpuhash_gen_inserts(ins.data_ptr(), None, SEED, pop + rank * (1 << 26) + N_INSERT * kd, N_INSERT * ke, be._stream()))
-    hi.copy_(ins[:ke].cpu())
-    ho = torch.empty((ke, N_SEARCH, 2), dtype=torch.int32).pin_memory()
-    ds = torch.empty((S, N_SEARCH, 2), dtype=torch.int32, device=dev); di = torch.empty((S, N_INSERT, 3), dtype=torch.int32, device=dev)
-    do = torch.empty((S, N_SEARCH, 2), dtype=torch.int32, device=dev)
+    hi.copy_(ins_f[: ke * N_INSERT].cpu())
+    ho = torch.empty((ke * N_SEARCH, 2), dtype=torch.int32).pin_memory()
+    Se = min(S, 4)
+    ds = torch.empty((Se, GROUP * N_SEARCH, 2), dtype=torch.int32, device=dev); di = torch.empty((Se, GROUP * N_INSERT, 3), dtype=torch.int32, device=dev)
+    do = torch.empty((Se, GROUP * N_SEARCH, 2), dtype=torch.int32, device=dev)
 
     def e2e(count):
         torch.cuda.synchronize(); dist.barrier()
@@ -181,13 +198,17 @@ def main(args, rank, world, local_rank, log):
         cur = torch.cuda.current_stream()
         for st in streams:
             st.wait_stream(cur)
-        Se = min(S, 8)              # call-by-call launches: at most as many lanes as hardware queues
-        for i in range(count):
-            k, b = i % Se, i % ke
+        c, i = 0, 0
+        while i < count:
+            b = i % ke
+            g = min(GROUP, count - i, ke - b)
+            k = c % Se
             with torch.cuda.stream(streams[k]):
-                ds[k].copy_(hs[b], non_blocking=True); di[k].copy_(hi[b], non_blocking=True)
-                lanes[k].search(ds[k], do[k]); lanes[k].insert(di[k])
-                ho[b].copy_(do[k], non_blocking=True)
+                ds[k][: g * N_SEARCH].copy_(hs[b * N_SEARCH:(b + g) * N_SEARCH], non_blocking=True)
+                di[k][: g * N_INSERT].copy_(hi[b * N_INSERT:(b + g) * N_INSERT], non_blocking=True)
+                lanes[k].search(ds[k][: g * N_SEARCH], do[k][: g * N_SEARCH]); lanes[k].insert(di[k][: g * N_INSERT])
+                ho[b * N_SEARCH:(b + g) * N_SEARCH].copy_(do[k][: g * N_SEARCH], non_blocking=True)
+            c += 1; i += g
         for st in streams:
             cur.wait_stream(st)
         e1.record(); torch.cuda.synchronize()
@@ -195,10 +216,10 @@ def main(args, rank, world, local_rank, log):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    e2e(min(ke, 20))
+    e2e(min(ke, 2 * GROUP))
+    e_steps = min(steps, ke)
     with sampler:
-        t_e = e2e(steps if steps <= ke else ke)
-    e_steps = steps if steps <= ke else ke
+        t_e = e2e(e_steps)
     e2e_val = world * e_steps * BATCH / t_e / 1e6
 
     if rank == 0:
@@ -210,6 +231,7 @@ def main(args, rank, world, local_rank, log):
                            f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
                            f"per GPU and step {N_SEARCH} searches + {N_INSERT} inserts")
         cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph, "lanes": S,
+                    "batches_per_exchange": GROUP, "wait_mode": "stream mem-ops" if L.gpuhash_wait_mode() == 1 else "kernel",
                     "parallelism": f"shard{world}"})
         line = {
             "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)", "value": round(value, 1), "unit": "Mops/s",
@@ -217,7 +239,7 @@ def main(args, rank, world, local_rank, log):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
                     "d2h_bytes_per_step": 8 * N_SEARCH, "steps": e_steps},
-            "gpu_launches": steps * 10,
+            "gpu_launches": -(-steps // GROUP) * 5,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": None, "kernel": "search_segments_kernel (per GPU, routed)", "peak_source": peak_src,
                          "note": "search path only, includes both NVLink exchanges"},
