@@ -202,7 +202,7 @@ def main():
             run_reference_arm(args, log)
         return 0
 
-    if world > 1:
+    if world > 1 or os.environ.get("GPUHASH_FORCE_SHARDED"):      # (the env switch: routed path on one GPU, for profiling)
         from megakv_b200 import sharded_bench                     # multi-GPU arm: sharded index + all-to-all routing
         return sharded_bench.main(args, rank, world, local_rank, log)
 

@@ -230,7 +230,12 @@ __device__ __forceinline__ bool last_cta_done(uint32_t *ticket)
 	return last != 0;
 }
 
-template <int kWords>
+/* Slot allocation is warp-aggregated: the lanes of a warp that go to the same owner are found with
+ * __match_any_sync, their leader takes one shared-memory atomic for all of them (G <= 8 atomics per warp instead
+ * of 32 on one or two hot counters), one global atomic per (CTA, owner) reserves the CTA's run in the owner's
+ * region, and the run is written in slot order so that the stores of neighbouring lanes coalesce -- over NVLink
+ * when the owner is a peer.  kItems requests per thread and tile amortise the three barriers. */
+template <int kWords, int kItems>
 __global__ void __launch_bounds__(256)
 route_scatter_pub_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t hash_mask_total, int shift, int G,
 		Ptrs dst, uint32_t *counts2 /* [2][8] */, uint32_t *perm, size_t cap, PubArgs pub,
@@ -239,44 +244,60 @@ route_scatter_pub_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t has
 	__shared__ uint32_t blk_count[kMaxShards], blk_base[kMaxShards];
 	__shared__ int ok;
 	uint32_t *counts = counts2 + 8 * (pub.seq & 1u);
+	const unsigned lane = threadIdx.x & 31u;
 	if (threadIdx.x == 0) {
 		ok = 1;
 		if (ack_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(ack_flags + s, pub.seq - 1u, 2000000000ULL, err);
 	}
 	__syncthreads();
 	if (ok) {
-		for (size_t tile = (size_t)blockIdx.x * blockDim.x; tile < n; tile += (size_t)gridDim.x * blockDim.x) {
+		const size_t tile_sz = (size_t)blockDim.x * kItems;
+		for (size_t tile = (size_t)blockIdx.x * tile_sz; tile < n; tile += (size_t)gridDim.x * tile_sz) {
 			if (threadIdx.x < kMaxShards) blk_count[threadIdx.x] = 0;
 			__syncthreads();
-			const size_t i = tile + threadIdx.x;
-			uint32_t w[kWords]; uint32_t d = 0, rank = 0;
-			if (i < n) {
+			uint32_t w[kItems][kWords]; uint32_t d[kItems], rank[kItems];
 #pragma unroll
-				for (int k = 0; k < kWords; k++) w[k] = gh::ld_stream_u32(in + kWords * i + k);
-				d = (w[1] & hash_mask_total) >> shift;
-				rank = atomicAdd(&blk_count[d], 1u);
+			for (int it = 0; it < kItems; it++) {
+				const size_t i = tile + (size_t)it * blockDim.x + threadIdx.x;
+				const bool live = i < n;
+				d[it] = 0xffu; rank[it] = 0;
+				if (live) {
+#pragma unroll
+					for (int k = 0; k < kWords; k++) w[it][k] = gh::ld_stream_u32(in + kWords * i + k);
+					d[it] = (w[it][1] & hash_mask_total) >> shift;
+				}
+				const unsigned peers = __match_any_sync(0xffffffffu, d[it]);       /* lanes with the same owner */
+				const int leader = __ffs(peers) - 1;
+				uint32_t base = 0;
+				if (live && (int)lane == leader) base = atomicAdd(&blk_count[d[it]], (uint32_t)__popc(peers));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				rank[it] = base + __popc(peers & ((1u << lane) - 1u));
 			}
 			__syncthreads();
 			if (threadIdx.x < G && blk_count[threadIdx.x])
 				blk_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], blk_count[threadIdx.x]);
 			__syncthreads();
-			if (i < n) {
-				const size_t slot = (size_t)blk_base[d] + rank;
-				uint32_t *q = (uint32_t *)dst.p[d] + kWords * slot;
 #pragma unroll
-				for (int k = 0; k < kWords; k++) q[k] = w[k];
-				if (perm) perm[(size_t)d * cap + slot] = (uint32_t)i;
+			for (int it = 0; it < kItems; it++) {
+				const size_t i = tile + (size_t)it * blockDim.x + threadIdx.x;
+				if (i < n) {
+					const size_t slot = (size_t)blk_base[d[it]] + rank[it];
+					uint32_t *q = (uint32_t *)dst.p[d[it]] + kWords * slot;
+					if (kWords == 2) *reinterpret_cast<uint2 *>(q) = make_uint2(w[it][0], w[it][1]);
+					else { q[0] = w[it][0]; q[1] = w[it][1]; q[kWords - 1] = w[it][kWords - 1]; }
+					if (perm) perm[(size_t)d[it] * cap + slot] = (uint32_t)i;
+				}
 			}
 			__syncthreads();
 		}
 	}
 	if (last_cta_done(pub.ticket)) {
 		if (threadIdx.x < G) {
-			const int d = threadIdx.x;
-			const uint32_t c = ((volatile uint32_t *)counts)[d];
-			((volatile uint32_t *)pub.peer_count.p[d])[pub.my_rank] = c;
+			const int dd = threadIdx.x;
+			const uint32_t c = ((volatile uint32_t *)counts)[dd];
+			((volatile uint32_t *)pub.peer_count.p[dd])[pub.my_rank] = c;
 			__threadfence_system();
-			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[d] + pub.my_rank), "r"(pub.seq) : "memory");
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[dd] + pub.my_rank), "r"(pub.seq) : "memory");
 		}
 		if (threadIdx.x < kMaxShards) counts2[8 * ((pub.seq + 1u) & 1u) + threadIdx.x] = 0;   /* next batch's counters */
 		if (threadIdx.x == 0) *pub.ticket = 0;
@@ -560,12 +581,20 @@ extern "C" int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_wo
 	int bits = 0; while ((hash_mask_total >> bits) & 1u) bits++;
 	const int shift = bits - log2_shards;
 	if (shift < 0) return -1;
-	const unsigned blocks = grid_for(n ? n : 1, 16);
 	cudaStream_t s = (cudaStream_t)stream;
-	if (elem_words == 2)
-		route_scatter_pub_kernel<2><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
-	else
-		route_scatter_pub_kernel<3><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+	if (n <= ((size_t)1 << 17)) {                     /* small batch: one request per thread, as many CTAs as possible */
+		const unsigned blocks = grid_for(n ? n : 1, 16);
+		if (elem_words == 2)
+			route_scatter_pub_kernel<2, 1><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+		else
+			route_scatter_pub_kernel<3, 1><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+	} else {
+		const unsigned blocks = grid_for((n + 3) / 4, 16);
+		if (elem_words == 2)
+			route_scatter_pub_kernel<2, 4><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+		else
+			route_scatter_pub_kernel<3, 4><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
+	}
 	return (int)cudaGetLastError();
 }
 

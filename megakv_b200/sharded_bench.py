@@ -30,7 +30,11 @@ def main(args, rank, world, local_rank, log):
 
     torch.cuda.set_device(local_rank)
     N.check(mk.lib().gpuhash_set_device(local_rank))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if "RANK" not in os.environ:                                  # single process (profiling the routed kernels on one GPU)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = mk.lib()
     dev = torch.device("cuda", local_rank)
     steps, warm = max(1, args.steps), max(3, args.warmup)
