@@ -490,37 +490,43 @@ extern "C" int gpuhash_wait_flags(const uint32_t *flags_d, int num, uint32_t wan
 }
 extern "C" int gpuhash_wait_mode(void) { if (g_wait_mode < 0) resolve_wait_mode(); return g_wait_mode; }
 
-/* serve, op 0, four lanes per request: each bucket of a routed request is ONE L2 request (see search_quad_kernel) */
+/* serve, op 0, four lanes per request: each bucket of a routed request is ONE L2 request (see search_quad_kernel).
+ * A warp handles 8 consecutive requests of ONE source region (the request index space pads every region to a
+ * multiple of 8), and their 8 results leave as two aligned 32 B stores by two lanes: the staging area is
+ * peer-mapped memory, where ncu shows partial-sector stores costing a DRAM write each (73 B written per 8 B result
+ * before this). */
 template <bool kPairs>
 __global__ void __launch_bounds__(256)
 serve_search_quad_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, Ptrs seg_out,
 		const uint32_t *req_flags, uint32_t *err, PubArgs pub)
 {
-	__shared__ uint32_t prefix[kMaxShards + 1];
+	__shared__ uint32_t prefix[kMaxShards + 1], count[kMaxShards];
 	__shared__ int ok;
 	if (threadIdx.x == 0) {
 		ok = 1;
 		if (req_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
 		uint32_t acc = 0;
-		for (int s = 0; s < G; s++) { prefix[s] = acc; acc += ((const volatile uint32_t *)seg_count)[s]; }
+		for (int s = 0; s < G; s++) {
+			const uint32_t c = ((const volatile uint32_t *)seg_count)[s];
+			prefix[s] = acc; count[s] = c; acc += (c + 7u) & ~7u;
+		}
 		prefix[G] = acc;
 	}
 	__syncthreads();
 	if (ok) {
 		const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
-		const uint32_t total = prefix[G], total_up = (total + 7u) & ~7u;
+		const uint32_t total = prefix[G];                                 /* multiple of 8 */
 		const uint32_t per_iter = (gridDim.x * blockDim.x) >> 2;
 		int s = 0;
-		for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; e < total_up; e += per_iter) {
-			const bool live = e < total;
+		for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; e < total; e += per_iter) {
+			while (e >= prefix[s + 1]) s++;
+			const uint32_t j = e - prefix[s];
+			const bool live = j < count[s];
 			uint2 q = make_uint2(0u, 0u);
 			gh::Row r;
 #pragma unroll
 			for (int k = 0; k < 8; k++) r.w[k] = 0;
-			uint32_t j = 0;
 			if (live) {
-				while (e >= prefix[s + 1]) s++;
-				j = e - prefix[s];
 				q = ld_u2_sys((const uint2 *)seg_in.p[s] + j);
 				const uint32_t b = sub < 2 ? gh::bucket1(g, q.y) : gh::bucket2(g, q.y, q.x);
 				r = gh::ld_row_ro(table[b].w + 8 * half);
@@ -549,7 +555,25 @@ serve_search_quad_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G
 				if (!msig) loc = 0;
 				o = make_uint2(__shfl_sync(0xffffffffu, loc, grp0 + 1), __shfl_sync(0xffffffffu, loc, grp0 + 3));
 			}
-			if (live && sub == 0) ((uint2 *)seg_out.p[s])[j] = o;
+			/* request k of this warp (k = 0..7) has its result on lane 4k; lanes 0 and 1 collect four each */
+			uint32_t v[8];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const int src = 16 * (int)(lane & 1u) + 4 * k;
+				v[2 * k] = __shfl_sync(0xffffffffu, o.x, src);
+				v[2 * k + 1] = __shfl_sync(0xffffffffu, o.y, src);
+			}
+			if (lane < 2) {
+				const uint32_t j0 = (e - (lane >> 2)) - prefix[s] + 4 * lane;   /* e of lane 0/1 is the warp's first request */
+				uint32_t *dstp = (uint32_t *)seg_out.p[s] + 2 * (size_t)j0;
+				if (j0 + 4 <= count[s]) {
+					asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(dstp),
+						"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+				} else {
+					for (int k = 0; k < 4; k++)
+						if (j0 + k < count[s]) *reinterpret_cast<uint2 *>(dstp + 2 * k) = make_uint2(v[2 * k], v[2 * k + 1]);
+				}
+			}
 		}
 	}
 	if (last_cta_done(pub.ticket)) {

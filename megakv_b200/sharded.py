@@ -109,7 +109,7 @@ class CudaShardBackend:
         from . import _native as N
         from .hashindex import DeviceBuffer, make_geom
         self.torch, self.N, self.L = torch, N, N.lib()
-        self.plan, self.rank, self.cap, self.G = plan, rank, int(cap), plan.world
+        self.plan, self.rank, self.cap, self.G = plan, rank, (int(cap) + 7) & ~7, plan.world     # regions stay 32 B aligned
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.geom = make_geom(plan.mem_p_total, algo, plan.log2, layout)
         # several backends ("lanes": independent buffer sets for batches in flight) may share one shard table

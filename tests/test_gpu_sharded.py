@@ -70,18 +70,21 @@ def _worker(rank, world, port, exchange, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [1, 2])
 @pytest.mark.parametrize("exchange", ["collective", "p2p"])
-def test_sharded_two_gpus(gpu, exchange):
-    if gpu.lib().gpuhash_device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_sharded_index_on_gpus(gpu, exchange, world):
+    """world 1: the whole routed path (scatter, publish, wait, serve, gather) with this GPU as its own peer, so a
+    1-GPU box still runs every kernel of the sharded index; world 2: across NVLink."""
+    if gpu.lib().gpuhash_device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, exchange, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
         assert p.exitcode == 0, "a rank failed"
-    assert sorted(ret.keys()) == [0, 1]
+    assert sorted(ret.keys()) == list(range(world))

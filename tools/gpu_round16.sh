@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 echo "== routed path on ONE GPU (all exchanges local): quick value + per-kernel times"
-GPUHASH_FORCE_SHARDED=1 GPUHASH_BENCH_QUICK=1 timeout 300 python bench.py --steps 640 --warmup 32 2>gpurun_out/r16.err | grep quick || tail -5 gpurun_out/r16.err
-GPUHASH_FORCE_SHARDED=1 GPUHASH_BENCH_QUICK=1 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests_srcunit_tex.sum --clock-control none -k regex:"serve|scatter|gather" -c 60 --csv --log-file gpurun_out/ncu_routed.csv python bench.py --steps 64 --warmup 16 --graph 0 > /dev/null 2>&1
+GPUHASH_FORCE_SHARDED=1 GPUHASH_BENCH_QUICK=1 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests_srcunit_tex.sum --clock-control none -k regex:"serve_search|gather|scatter_pub_kernel<2" -c 30 --csv --log-file gpurun_out/ncu_routed.csv python bench.py --steps 64 --warmup 16 --graph 0 > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
 rows=[r for r in csv.reader(open('gpurun_out/ncu_routed.csv')) if len(r)>10]
