@@ -643,6 +643,150 @@ search_quad_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 	}
 }
 
+/* ---- four lanes per request + the batch staged through shared memory by bulk copies (TMA 1-D) ---- */
+
+// The request batch and the result batch are moved 64 requests (512 B) at a time by cp.async.bulk: one elected
+// thread asks the copy unit for the tile's queries (global -> shared, completion on an mbarrier), every 4-lane
+// group reads its query from shared memory, and the 64 results leave as one 512 B bulk store (shared -> global).
+// Why: (1) the batches may live in the caller's PINNED HOST buffers (gpuhash_index_set_zero_copy) -- over PCIe a
+// warp's 64 B query load / 64 B result store are 64 B transactions and the link tops out at ~21 GB/s per direction
+// (tools/pcie_probe), 512 B transfers keep it at the 40+ GB/s large copies reach; (2) in HBM it halves the L2
+// requests spent on the streams (0.25 -> 0.125 per search) and takes both off the LSU path.  Two stages: the
+// queries of the CTA's next tile are in flight while this one is probed; the store of tile t drains while t+1 runs.
+// Needs 16 B-aligned tiles: `head` (0 or 1) leading requests are done the plain way so that in + head is aligned;
+// out_bulk says whether out + head is too (else results are stored per request).  The last, partial tile is plain.
+constexpr int kTileReq = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while (!done);
+}
+
+template <bool kPairs>
+__device__ __forceinline__ uint2 quad_probe(const Bucket* __restrict__ table, const Geom& g, uint2 q, bool live,
+		unsigned sub, unsigned grp0, unsigned half, uint32_t& hit1, uint32_t& hit2)
+{
+	Row r;
+#pragma unroll
+	for (int k = 0; k < 8; k++) r.w[k] = 0;
+	if (live) {
+		const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
+		r = ld_row_ro(table[b].w + 8 * half);
+	}
+	if (kPairs) {                                                // this lane holds slots 4*half .. 4*half+3 as {sig, loc}
+		uint32_t m = (r.w[0] == q.x ? 1u : 0u) | (r.w[2] == q.x ? 2u : 0u) | (r.w[4] == q.x ? 4u : 0u) | (r.w[6] == q.x ? 8u : 0u);
+		const uint32_t loc = (m & 1u) ? r.w[1] : (m & 2u) ? r.w[3] : (m & 4u) ? r.w[5] : r.w[7];
+		if (!live) m = 0;
+		const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));   // lowest slot wins
+		const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
+		hit1 = hits & 3u; hit2 = hits & 12u;
+		return make_uint2(hit1 ? l0 : 0u, hit2 ? l1 : 0u);
+	} else {                                                     // even lanes hold a signature row, odd lanes its location row
+		const uint32_t m = live ? eq_mask(r, q.x) : 0u;
+		const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));
+		const int l = __ffs(msig | 0x100u) - 1 & 7;
+		uint32_t loc = r.w[0];
+		if (l == 1) loc = r.w[1];
+		if (l == 2) loc = r.w[2];
+		if (l == 3) loc = r.w[3];
+		if (l == 4) loc = r.w[4];
+		if (l == 5) loc = r.w[5];
+		if (l == 6) loc = r.w[6];
+		if (l == 7) loc = r.w[7];
+		if (!msig) loc = 0;
+		const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + 1);
+		const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + 3);
+		hit1 = __shfl_sync(0xffffffffu, m, grp0);
+		hit2 = __shfl_sync(0xffffffffu, m, grp0 + 2);
+		return make_uint2(l0, l1);
+	}
+}
+
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
+		const Bucket* __restrict__ table, size_t n, Geom g, Stats* st, unsigned head, int out_bulk)
+{
+	__shared__ __align__(128) uint2 q_s[2][kTileReq];
+	__shared__ __align__(128) uint2 o_s[2][kTileReq];
+	__shared__ __align__(8) unsigned long long bar[2];
+	const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
+	const unsigned quad = threadIdx.x >> 2;                      // 0..63: this group's request inside the tile
+	uint32_t h1, h2;
+
+	if (head && blockIdx.x == 0 && threadIdx.x < 32) {           // the request in front of the first aligned tile
+		const bool live = lane < 4;
+		const uint2 q = live ? ld_stream_u2(in) : make_uint2(0u, 0u);
+		const uint2 o = quad_probe<kPairs>(table, g, q, live, sub, grp0, half, h1, h2);
+		if (lane == 0) {
+			st_stream_u2(out, o);
+			if (st) { if (h1) atomicAdd(&st->search_hits_b1, 1ULL); if (h2) atomicAdd(&st->search_hits_b2, 1ULL); }
+		}
+	}
+	const uint2* in_a = in + head; uint2* out_a = out + head;
+	const size_t n_a = n - head;
+	const size_t tiles = (n_a + kTileReq - 1) / kTileReq;
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[0])));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[1])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	// tile t is "full" when all 64 requests exist: only full tiles go through the copy unit
+	auto issue_load = [&](size_t t, int s) {
+		const uint32_t b = smem_u32(&bar[s]);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(kTileReq * 8) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(&q_s[s][0])), "l"(in_a + t * kTileReq), "r"(kTileReq * 8), "r"(b) : "memory");
+	};
+	size_t t = blockIdx.x;
+	if (threadIdx.x == 0 && t < tiles && (t + 1) * kTileReq <= n_a) issue_load(t, 0);
+	uint32_t it = 0;
+	bool store_pending = false;                                  // thread 0 only
+	for (; t < tiles; t += gridDim.x, it++) {
+		const int s = (int)(it & 1u);
+		const bool full = (t + 1) * kTileReq <= n_a;
+		const size_t tn = t + gridDim.x;
+		if (threadIdx.x == 0 && tn < tiles && (tn + 1) * kTileReq <= n_a) issue_load(tn, s ^ 1);
+		const size_t i = t * kTileReq + quad;
+		const bool live = i < n_a;
+		uint2 q = make_uint2(0u, 0u);
+		if (full) {
+			mbar_wait(smem_u32(&bar[s]), (it >> 1) & 1u);
+			q = q_s[s][quad];
+		} else if (live) {
+			q = ld_stream_u2(in_a + i);
+		}
+		const uint2 o = quad_probe<kPairs>(table, g, q, live, sub, grp0, half, h1, h2);
+		const bool bulk = full && out_bulk;
+		if (live && sub == 0) {
+			if (bulk) o_s[s][quad] = o; else st_stream_u2(out_a + i, o);
+			if (st) { if (h1) atomicAdd(&st->search_hits_b1, 1ULL); if (h2) atomicAdd(&st->search_hits_b2, 1ULL); }
+		}
+		// o_s[s] was the source of the bulk store issued two iterations ago; o_s[s^1] of the one issued last
+		// iteration: thread 0 makes sure that one has been read out before anyone passes the barrier, because
+		// the next iteration writes o_s[s^1] again.
+		if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		if (threadIdx.x == 0 && store_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); store_pending = false; }
+		__syncthreads();
+		if (threadIdx.x == 0 && bulk) {
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+				:: "l"(out_a + t * kTileReq), "r"(smem_u32(&o_s[s][0])), "r"(kTileReq * 8) : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			store_pending = true;
+		}
+	}
+	if (threadIdx.x == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 /* ---- one launch per scheduler cycle: search -> delete -> insert ---- */
 
 // The reference issues three launches per worker and cycle, stream-ordered search -> delete -> insert

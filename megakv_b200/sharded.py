@@ -191,32 +191,19 @@ class CudaShardBackend:
 
     # -- fused path: symmetric arena per rank, exported over CUDA IPC
     #    layout: inbox [G][cap][3] i32 | stage [G][cap][2] i32 | inbox_count [8] | req_flag [8] | res_flag [8] | err [8]
-    def p2p_setup(self, ix):
+    def _arena_alloc(self):
         from .hashindex import DeviceBuffer
-        t, L, N = self.torch, self.L, self.N
         G, cap = self.G, self.cap
         self.off_inbox, self.off_stage = 0, G * cap * 12
         self.off_cnt = self.off_stage + G * cap * 8
         self.off_reqf, self.off_resf, self.off_err = self.off_cnt + 32, self.off_cnt + 64, self.off_cnt + 96
         self.off_cnt2, self.off_ticket = self.off_cnt + 128, self.off_cnt + 192     # local only: counters [2][8], tickets [2]
         self.arena = DeviceBuffer(self.off_cnt + 256, zero=True)
-        handle = (C.c_ubyte * 64)()
-        N.check(L.gpuhash_ipc_export(self.arena.ptr, handle), "cudaIpcGetMemHandle")
-        mine = t.tensor(list(handle), dtype=t.uint8, device=self.dev)
-        allh = [t.empty_like(mine) for _ in range(G)]
-        ix.dist.all_gather(allh, mine, group=ix.group)
-        self.peer = []
-        for r in range(G):
-            if r == self.rank:
-                self.peer.append(self.arena.ptr)
-            else:
-                raw = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
-                p = L.gpuhash_ipc_import(raw)
-                if not p:
-                    raise N.GpuHashError(f"cudaIpcOpenMemHandle failed for rank {r}")
-                self.peer.append(p)
-        ix.dist.barrier(group=ix.group)
-        # constant pointer tables of the fused path
+
+    def _set_peers(self, peer):
+        """peer[r] = address of rank r's arena in THIS process (own, CUDA IPC import, or -- LocalCluster -- plain)"""
+        t = self.torch
+        self.peer = list(peer)
         G, cap, r = self.G, self.cap, self.rank
         self.pp_peer_inbox = self._ptrs([self.peer[d] + self.off_inbox + r * cap * 12 for d in range(G)])
         self.pp_peer_cnt = self._ptrs([self.peer[d] + self.off_cnt for d in range(G)])
@@ -229,6 +216,28 @@ class CudaShardBackend:
                                        + [0] * (MAX_SHARDS - G), dtype=t.int64))
         t.cuda.synchronize()
         self.p2p = True
+
+    def p2p_setup(self, ix):
+        t, L, N = self.torch, self.L, self.N
+        G = self.G
+        self._arena_alloc()
+        handle = (C.c_ubyte * 64)()
+        N.check(L.gpuhash_ipc_export(self.arena.ptr, handle), "cudaIpcGetMemHandle")
+        mine = t.tensor(list(handle), dtype=t.uint8, device=self.dev)
+        allh = [t.empty_like(mine) for _ in range(G)]
+        ix.dist.all_gather(allh, mine, group=ix.group)
+        peer = []
+        for r in range(G):
+            if r == self.rank:
+                peer.append(self.arena.ptr)
+            else:
+                raw = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                p = L.gpuhash_ipc_import(raw)
+                if not p:
+                    raise N.GpuHashError(f"cudaIpcOpenMemHandle failed for rank {r}")
+                peer.append(p)
+        ix.dist.barrier(group=ix.group)
+        self._set_peers(peer)
 
     # Waits are separate one-CTA launches (gpuhash_wait_flags): a CTA that waits inside a big kernel keeps an SM slot,
     # and with many lanes in flight two GPUs can fill up with CTAs waiting for each other's producers.
@@ -263,11 +272,15 @@ class CudaShardBackend:
         self._p2p_serve(ix, 0, 2 * max(n, 1))           # uniform keys: about n requests arrive; the grid strides if more do
         if out is None:
             out = self.empty(n, 2)
+        self._p2p_gather(ix, n, out)
+        return out
+
+    def _p2p_gather(self, ix, n, out):
+        L, N, A = self.L, self.N, self.arena.ptr
         self._wait(self.off_resf, ix.seq)
         N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), A + self.off_cnt2 + 32 * (ix.seq & 1), self.cap,
                                        self.plan.log2, out.data_ptr() if n else None, n, None, 0, None, self._stream()),
                 "gpuhash_route_gather")
-        return out
 
     def p2p_update(self, ix, iel, insert):
         """scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter."""
@@ -277,3 +290,61 @@ class CudaShardBackend:
     def p2p_error(self):
         """1 if a flag wait timed out (a peer died); checked by the callers after synchronising"""
         return int(self.arena.download(np.uint32)[self.off_err // 4])
+
+
+class _Seq:
+    """what the fused path needs from its ShardedIndex: the batch sequence number"""
+    def __init__(self):
+        self.seq = 0
+
+
+class LocalCluster:
+    """G virtual ranks on ONE GPU in one process: every rank has its own shard table and arena, "peer" pointers are
+    plain device pointers.  The kernels, flags and buffer layout are exactly those of the multi-process fused path;
+    what is missing is NVLink.  Used (a) by the GPU tests, so that a 1-GPU box exercises G = 2, 4, 8, and (b) to
+    measure what the routed path costs per GPU without paying for eight of them.
+
+    One call = one exchange of all ranks, issued phase by phase on the current stream (all scatters, all serves,
+    all gathers): stream order alone satisfies every flag, so nothing can wait for work that is queued behind it."""
+
+    def __init__(self, plan, cap, algo=0, layout=0, tables=None):
+        self.plan, self.G = plan, plan.world
+        self.be = [CudaShardBackend(plan, r, cap, algo, layout, table=tables[r] if tables else None) for r in range(self.G)]
+        for b in self.be:
+            b._arena_alloc()
+        for b in self.be:
+            b._set_peers([x.arena.ptr for x in self.be])
+        self.ix = [_Seq() for _ in range(self.G)]
+
+    @property
+    def tables(self):
+        return [b.table for b in self.be]
+
+    def search(self, sels, outs=None):
+        """sels[r]: rank r's requests, int32 [n_r, 2]; returns (or fills) outs[r] int32 [n_r, 2]"""
+        be, ix, G = self.be, self.ix, self.G
+        for r in range(G):
+            be[r]._p2p_scatter(ix[r], sels[r], 2, True)
+        for r in range(G):
+            be[r]._p2p_serve(ix[r], 0, 2 * max(max(s.shape[0] for s in sels), 1))
+        if outs is None:
+            outs = [be[r].empty(sels[r].shape[0], 2) for r in range(G)]
+        for r in range(G):
+            be[r]._p2p_gather(ix[r], sels[r].shape[0], outs[r])
+        return outs
+
+    def update(self, reqs, insert=True):
+        be, ix, G = self.be, self.ix, self.G
+        for r in range(G):
+            be[r]._p2p_scatter(ix[r], reqs[r], 3, False)
+        for r in range(G):
+            be[r]._p2p_serve(ix[r], 1 if insert else 2, 2 * max(max(q.shape[0] for q in reqs), 1))
+
+    def insert(self, reqs):
+        self.update(reqs, True)
+
+    def delete(self, reqs):
+        self.update(reqs, False)
+
+    def error(self):
+        return sum(b.p2p_error() for b in self.be)

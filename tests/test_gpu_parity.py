@@ -93,7 +93,7 @@ def test_search_ragged_sizes(gpu, layout, n, rng):
     assert np.array_equal(gpu_search(t, sel, prezero=False), o.search(sel))
 
 
-@pytest.mark.parametrize("qpt", [1, 2, 4, -1, -4])
+@pytest.mark.parametrize("qpt", [1, 2, 4, -1, -4, -5])
 @pytest.mark.parametrize("split_mode", [1, 2])
 def test_search_every_launch_variant(gpu, layout, qpt, split_mode, rng):
     o = po.Oracle(20)
@@ -107,6 +107,78 @@ def test_search_every_launch_variant(gpu, layout, qpt, split_mode, rng):
         assert np.array_equal(gpu_search(t, sel, prezero=False), o.search(sel))
     finally:
         N.lib().gpuhash_set_tuning(old)
+
+
+@pytest.mark.parametrize("in_off,out_off", [(0, 0), (1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 128, 129, 4097, 62259, 300001])
+def test_search_staged_kernel_alignment_and_tails(gpu, layout, n, in_off, out_off, rng):
+    """search_quad_staged_kernel moves the batch in 512 B bulk copies, which need 16 B-aligned tiles: request and
+    result arrays that start on an odd 8 B boundary (every second batch of bench.py does: 62259 * 8 is not a multiple
+    of 16), a lone head request, partial last tiles, more tiles than CTAs -- all bit-exact against the oracle, and
+    nothing outside out[0 .. 2n) is written."""
+    o = po.Oracle(18)
+    iel = H.random_requests(rng, 20000)
+    o.insert(iel)
+    t = table_from_oracle(o, layout)
+    sel = np.concatenate([H.to_sel(iel), H.to_sel(H.random_requests(rng, 5000))])[rng.integers(0, 25000, n)]
+    in_d = mk.DeviceBuffer(8 * (n + 4)); out_d = mk.DeviceBuffer(8 * (n + 4))
+    pad = np.zeros(n + 4, dtype=mk.SEL_DT); pad[in_off:in_off + n] = sel
+    in_d.upload(pad)
+    out_d.upload(np.full(2 * (n + 4), 0xDEADBEEF, dtype=np.uint32))
+    old = N.Tune(); N.lib().gpuhash_get_tuning(old)
+    try:
+        N.lib().gpuhash_set_tuning(N.Tune(-5, 0, 4))
+        N.check(N.lib().gpuhash_search_ex(C.byref(t.geom), in_d.ptr + 8 * in_off, out_d.ptr + 8 * out_off, t.ptr, n, None, None))
+        mk.device_sync()
+    finally:
+        N.lib().gpuhash_set_tuning(old)
+    got = out_d.download(np.uint32)
+    assert np.array_equal(got[2 * out_off:2 * (out_off + n)], o.search(sel))
+    assert np.all(got[:2 * out_off] == 0xDEADBEEF) and np.all(got[2 * (out_off + n):] == 0xDEADBEEF)
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_index_zero_copy_submit_matches_oracle(gpu, layout, fused, rng):
+    """gpuhash_index_set_zero_copy: the kernels read requests from and write results to PINNED HOST buffers themselves
+    (bulk copies over the host link).  Same results as the staged-copy path and as the oracle."""
+    L = N.lib()
+    mem_p, graph_like_batches = 20, 3
+    old = N.Tune(); L.gpuhash_get_tuning(old)
+    L.gpuhash_set_tuning(N.Tune(0, 0, 4, fused))                  # 0: search/delete/insert launches (staged search kernel)
+    o = po.Oracle(mem_p)
+    ix = mk.GpuHashIndex(mem_p, workers=2, max_search=1 << 17, max_insert=1 << 16, max_delete=1 << 16, layout=layout)
+    base = H.random_requests(rng, 60000)
+    ix.insert(base); o.insert(base)
+    L.gpuhash_index_set_zero_copy(ix.h, 1)
+    n_s, n_i, n_d = 62259, 3277, 1000
+    hs = L.gpuhash_host_alloc(8 * n_s * graph_like_batches); ho = L.gpuhash_host_alloc(8 * n_s * graph_like_batches)
+    hi = L.gpuhash_host_alloc(12 * n_i * graph_like_batches); hd = L.gpuhash_host_alloc(12 * n_d * graph_like_batches)
+    assert hs and ho and hi and hd
+    try:
+        s_np = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_uint32)), shape=(graph_like_batches, 2 * n_s))
+        o_np = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_uint32)), shape=(graph_like_batches, 2 * n_s))
+        i_np = np.ctypeslib.as_array(C.cast(hi, C.POINTER(C.c_uint32)), shape=(graph_like_batches, 3 * n_i))
+        d_np = np.ctypeslib.as_array(C.cast(hd, C.POINTER(C.c_uint32)), shape=(graph_like_batches, 3 * n_d))
+        want = []
+        for b in range(graph_like_batches):                       # batch b: search, delete, insert -- in that order
+            fresh = H.random_requests(rng, n_i, loc_base=1000000 + b * n_i)
+            sel = np.concatenate([H.to_sel(base), H.to_sel(H.random_requests(rng, 5000))])[rng.integers(0, 65000, n_s)]
+            dele = base[b * n_d:(b + 1) * n_d]
+            s_np[b] = sel.view(np.uint32); i_np[b] = fresh.view(np.uint32).reshape(-1); d_np[b] = dele.view(np.uint32).reshape(-1)
+            want.append(o.search(sel)); o.delete(dele); o.insert(fresh)
+        o_np[:] = 0xDEADBEEF
+        for b in range(graph_like_batches):                       # one worker stream: batches stay ordered
+            N.check(L.gpuhash_index_submit(ix.h, 0, hs + 8 * n_s * b, n_s, ho + 8 * n_s * b, hd + 12 * n_d * b, n_d,
+                                           hi + 12 * n_i * b, n_i))
+        ix.sync()
+        for b in range(graph_like_batches):
+            assert np.array_equal(np.sort(o_np[b].reshape(-1, 2), 1), np.sort(want[b].reshape(-1, 2), 1)), f"batch {b}"
+        assert o.digest(table=ix.dump()) == o.digest()
+    finally:
+        L.gpuhash_set_tuning(old)
+        for p_ in (hs, ho, hi, hd):
+            L.gpuhash_host_free(p_)
+        ix.close()
 
 
 def test_search_py_search_stream_fixture(gpu, layout, rng):

@@ -88,3 +88,56 @@ def test_sharded_index_on_gpus(gpu, exchange, world):
         p.join(300)
         assert p.exitcode == 0, "a rank failed"
     assert sorted(ret.keys()) == list(range(world))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("layout", [0, 1], ids=["pairs", "reflayout"])
+def test_virtual_shards_on_one_gpu(gpu, world, layout):
+    """G = 2, 4, 8 virtual ranks on ONE GPU (megakv_b200.sharded.LocalCluster): the kernels, flags, regions and peer
+    pointer tables of the fused path exactly as the multi-process run uses them, minus NVLink -- so a 1-GPU box
+    checks every shard count against the single-table oracle: search words, deletes, and the shard tables
+    concatenated in rank order equal to the logical table as a multiset."""
+    import torch
+    import megakv_b200 as mk
+    from megakv_b200.sharded import ShardPlan, LocalCluster
+    from oracle import pyoracle as po
+    from tests import helpers as H
+    mk.lib().gpuhash_set_device(0); torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    mem_p, n = 24, 30000
+    plan = ShardPlan(mem_p, world)
+    cl = LocalCluster(plan, cap=1 << 16, layout=layout)
+    rng = np.random.default_rng(777 + world)
+    allk = H.random_requests(rng, world * n)
+    ref = po.Oracle(mem_p); ref.insert(allk)
+
+    def t3(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint32).reshape(-1, 3).view(np.int32).copy()).to(dev)
+
+    def t2(a):
+        return torch.from_numpy(np.ascontiguousarray(H.to_sel(a)).view(np.uint32).reshape(-1, 2).view(np.int32).copy()).to(dev)
+
+    for part in range(3):                                         # three exchanges: buffer reuse, flags, acks
+        cl.insert([t3(np.array_split(allk[r * n:(r + 1) * n], 3)[part]) for r in range(world)])
+    for rep in range(3):
+        probes = [np.concatenate([allk[(r + rep)::7], H.random_requests(rng, 500 + 13 * r)]) for r in range(world)]
+        if rep == 2:
+            probes[0] = probes[0][:0]                             # a rank with nothing to ask still takes part
+        outs = cl.search([t2(p) for p in probes])
+        for r in range(world):
+            got = outs[r].cpu().numpy().view(np.uint32)
+            want = ref.search(H.to_sel(probes[r])).reshape(-1, 2)
+            assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"search mismatch rank {r} rep {rep}"
+    victims = [allk[((r + 1) % world) * n:((r + 1) % world) * n + 2000] for r in range(world)]
+    cl.delete([t3(v) for v in victims])
+    for v in victims:
+        ref.delete(v)
+    outs = cl.search([t2(v) for v in victims])
+    torch.cuda.synchronize()
+    assert not any(o.cpu().numpy().any() for o in outs)
+    assert cl.error() == 0
+    parts = []
+    for b in cl.be:
+        t = mk.DeviceTable.__new__(mk.DeviceTable); t.geom, t.ptr, t.nbytes = b.geom, b.table.ptr, b.table.nbytes
+        parts.append(t.dump_reference()); t.ptr = None
+    assert ref.digest(table=np.concatenate(parts)) == ref.digest()
