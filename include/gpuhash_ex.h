@@ -208,6 +208,17 @@ int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_words, uint32
 		const void *const *dst_ptrs, uint32_t *counts2_d, uint32_t *perm_d, size_t cap, int my_rank,
 		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq,
 		const uint32_t *ack_flags_d, uint32_t *err_d, void *stream);
+/* Tile-sorted routing (the default of megakv_b200/sharded.py): every CTA sorts its tile of 1024 requests by owner in shared
+ * memory and writes each owner's run contiguously; map_d (gpuhash_route_map_bytes(cap) bytes, NULL for insert/delete
+ * batches) records per request its position in the sorted tile and per tile the run starts, which is all
+ * gpuhash_route_gather_tiles needs to bring the results (read run by run from the staging regions) back into request
+ * order with coalesced stores.  Publication as in gpuhash_route_scatter_pub; waits are the caller's (gpuhash_wait_flags). */
+size_t gpuhash_route_map_bytes(size_t cap);
+int gpuhash_route_scatter_tiles(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
+		const void *const *dst_ptrs, uint32_t *counts2_d, void *map_d, size_t cap, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq, void *stream);
+int gpuhash_route_gather_tiles(const void *const *staged_ptrs, const void *map_d, size_t cap, int log2_shards,
+		void *out_d, size_t n, void *stream);
 int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int log2_shards, const void *const *seg_in_ptrs,
 		const uint32_t *seg_count_d, const void *const *seg_out_ptrs, size_t max_total, const uint32_t *req_flags_d, uint32_t *err_d,
 		int my_rank, const void *const *peer_res_flag_ptrs, uint32_t *ticket_d, uint32_t seq, gpuhash_stats_t *stats_d, void *stream);

@@ -113,6 +113,9 @@ SYMBOLS = {
     "gpuhash_results_publish": (_i, [_i, _i, _vp, C.c_uint32, _vp]),
     "gpuhash_route_gather": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_delete_segments": (_i, [_gp, _vp, _i, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_route_map_bytes": (_sz, [_sz]),
+    "gpuhash_route_scatter_tiles": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, C.c_uint32, _vp]),
+    "gpuhash_route_gather_tiles": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
     "gpuhash_route_scatter_pub": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "gpuhash_serve": (_i, [_gp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _i, _vp, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_wait_flags": (_i, [_vp, _i, C.c_uint32, _vp, _vp]),

@@ -643,6 +643,8 @@ search_quad_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 	}
 }
 
+#endif  /* GH_DEFINE_KERNELS */
+
 /* ---- four lanes per request + the batch staged through shared memory by bulk copies (TMA 1-D) ---- */
 
 // The request batch and the result batch are moved 64 requests (512 B) at a time by cp.async.bulk: one elected
@@ -709,6 +711,7 @@ __device__ __forceinline__ uint2 quad_probe(const Bucket* __restrict__ table, co
 	}
 }
 
+#ifdef GH_DEFINE_KERNELS
 template <bool kPairs>
 __global__ void __launch_bounds__(256)
 search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
@@ -749,7 +752,7 @@ search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 	};
 	size_t t = blockIdx.x;
 	if (threadIdx.x == 0 && t < tiles && (t + 1) * kTileReq <= n_a) issue_load(t, 0);
-	uint32_t it = 0;
+	uint32_t it = 0, phases = 0;                                 // bit s of phases: parity of stage s's next completion
 	bool store_pending = false;                                  // thread 0 only
 	for (; t < tiles; t += gridDim.x, it++) {
 		const int s = (int)(it & 1u);
@@ -760,7 +763,8 @@ search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		const bool live = i < n_a;
 		uint2 q = make_uint2(0u, 0u);
 		if (full) {
-			mbar_wait(smem_u32(&bar[s]), (it >> 1) & 1u);
+			mbar_wait(smem_u32(&bar[s]), (phases >> s) & 1u);
+			phases ^= 1u << s;
 			q = q_s[s][quad];
 		} else if (live) {
 			q = ld_stream_u2(in_a + i);

@@ -349,11 +349,159 @@ serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *
 	}
 }
 
+/* ================= tile-sorted routing: scatter and gather that move whole runs =================
+ * route_scatter_pub_kernel stores each request from the lane that loaded it, so one warp store touches up to G
+ * runs of ~4 requests (32 B pieces), and route_gather_kernel un-permutes with one random 8 B store per result:
+ * about 0.5 and 1.1 L2 requests per search, on top of the 2.1 the lookup itself needs -- and requests are what the
+ * memory system counts (profiles/r01_l2_requests.md).  Here a CTA sorts its tile of kRouteTile requests by owner in
+ * shared memory first and writes each owner's run as one contiguous piece (128 requests = 1 KB on average at G = 8;
+ * full 128 B lines locally, large NVLink packets to peers).  What the gather needs to undo it is tiny: per tile the
+ * G run starts and lengths, per request its position in the sorted tile (16 bits).  The gather reads the G result
+ * runs of a tile contiguously into shared memory and writes the tile's results in request order, coalesced.
+ *   map layout: uint16 pos[cap_pad] | per tile { uint32 base[8], cnt[8] }          (cap_pad = cap rounded up to a tile) */
+constexpr int kRouteTile = 1024;
+
+__device__ __forceinline__ int run_of(const uint32_t *off, uint32_t q)      /* off[1..7]: run starts inside the sorted tile */
+{
+	return (int)(q >= off[1]) + (int)(q >= off[2]) + (int)(q >= off[3]) + (int)(q >= off[4])
+	     + (int)(q >= off[5]) + (int)(q >= off[6]) + (int)(q >= off[7]);
+}
+
+template <int kWords>
+__global__ void __launch_bounds__(256)
+route_scatter_tiles_kernel(const uint32_t *__restrict__ in, size_t n, uint32_t hash_mask_total, int shift, int G,
+		Ptrs dst, uint32_t *counts2 /* [2][8] */, uint16_t *pos, uint32_t *meta, PubArgs pub)
+{
+	constexpr int kItems = kRouteTile / 256;
+	__shared__ uint32_t cnt[kMaxShards], base[kMaxShards], off[kMaxShards + 1];
+	__shared__ uint32_t *dst_s[kMaxShards];
+	__shared__ __align__(16) uint32_t stage[kRouteTile * kWords];
+	uint32_t *counts = counts2 + 8 * (pub.seq & 1u);
+	const unsigned lane = threadIdx.x & 31u;
+	if (threadIdx.x < kMaxShards) dst_s[threadIdx.x] = (uint32_t *)dst.p[threadIdx.x];
+	const size_t tiles = (n + kRouteTile - 1) / kRouteTile;
+	for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		const size_t t0 = tile * kRouteTile;
+		const uint32_t tile_n = (uint32_t)(n - t0 < (size_t)kRouteTile ? n - t0 : (size_t)kRouteTile);
+		if (threadIdx.x < kMaxShards) cnt[threadIdx.x] = 0;
+		__syncthreads();
+		uint32_t w[kItems][kWords], d[kItems], rank[kItems];
+#pragma unroll
+		for (int it = 0; it < kItems; it++) {
+			const uint32_t k = it * 256 + threadIdx.x;
+			const bool live = k < tile_n;
+			d[it] = 0xffu; rank[it] = 0;
+			if (live) {
+				if (kWords == 2) {
+					const uint2 v = gh::ld_stream_u2((const uint2 *)in + t0 + k);
+					w[it][0] = v.x; w[it][1] = v.y;
+				} else {
+#pragma unroll
+					for (int j = 0; j < kWords; j++) w[it][j] = gh::ld_stream_u32(in + kWords * (t0 + k) + j);
+				}
+				d[it] = (w[it][1] & hash_mask_total) >> shift;           /* owner = top bits of bucket 1 (== of bucket 2) */
+			}
+			const unsigned peers = __match_any_sync(0xffffffffu, d[it]);
+			const int leader = __ffs(peers) - 1;
+			uint32_t b = 0;
+			if (live && (int)lane == leader) b = atomicAdd(&cnt[d[it]], (uint32_t)__popc(peers));
+			b = __shfl_sync(0xffffffffu, b, leader);
+			rank[it] = b + __popc(peers & ((1u << lane) - 1u));
+		}
+		__syncthreads();
+		if (threadIdx.x < kMaxShards) {
+			const uint32_t c = cnt[threadIdx.x];
+			base[threadIdx.x] = c ? atomicAdd(&counts[threadIdx.x], c) : 0u;   /* this tile's run in the owner's region */
+			uint32_t o = 0;
+			for (int j = 0; j < (int)threadIdx.x; j++) o += cnt[j];
+			off[threadIdx.x] = o;
+			if (threadIdx.x == kMaxShards - 1) off[kMaxShards] = o + c;
+			if (meta) { meta[tile * 16 + threadIdx.x] = base[threadIdx.x]; meta[tile * 16 + 8 + threadIdx.x] = c; }
+		}
+		__syncthreads();
+#pragma unroll
+		for (int it = 0; it < kItems; it++) {
+			const uint32_t k = it * 256 + threadIdx.x;
+			if (k < tile_n) {
+				const uint32_t p = off[d[it]] + rank[it];
+#pragma unroll
+				for (int j = 0; j < kWords; j++) stage[p * kWords + j] = w[it][j];
+				if (pos) pos[t0 + k] = (uint16_t)p;
+			}
+		}
+		__syncthreads();
+		for (uint32_t q = threadIdx.x; q < tile_n; q += 256) {           /* sorted order: neighbours share a run */
+			const int dd = run_of(off, q);
+			uint32_t *o = dst_s[dd] + (size_t)kWords * (base[dd] + q - off[dd]);
+			if (kWords == 2) *reinterpret_cast<uint2 *>(o) = make_uint2(stage[2 * q], stage[2 * q + 1]);
+			else { o[0] = stage[3 * q]; o[1] = stage[3 * q + 1]; o[2] = stage[3 * q + 2]; }
+		}
+		__syncthreads();
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G) {
+			const int dd = threadIdx.x;
+			const uint32_t c = ((volatile uint32_t *)counts)[dd];
+			((volatile uint32_t *)pub.peer_count.p[dd])[pub.my_rank] = c;
+			__threadfence_system();
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[dd] + pub.my_rank), "r"(pub.seq) : "memory");
+		}
+		if (threadIdx.x < kMaxShards) counts2[8 * ((pub.seq + 1u) & 1u) + threadIdx.x] = 0;   /* next batch's counters */
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+route_gather_tiles_kernel(Ptrs staged /* [G] -> uint2[cap] */, const uint16_t *__restrict__ pos, const uint32_t *__restrict__ meta,
+		uint2 *__restrict__ out, size_t n)
+{
+	__shared__ uint32_t base[kMaxShards], off[kMaxShards + 1];
+	__shared__ const uint2 *src_s[kMaxShards];
+	__shared__ __align__(16) uint2 stage[kRouteTile];
+	if (threadIdx.x < kMaxShards) src_s[threadIdx.x] = (const uint2 *)staged.p[threadIdx.x];
+	const size_t tiles = (n + kRouteTile - 1) / kRouteTile;
+	for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		const size_t t0 = tile * kRouteTile;
+		const uint32_t tile_n = (uint32_t)(n - t0 < (size_t)kRouteTile ? n - t0 : (size_t)kRouteTile);
+		__syncthreads();                                                  /* previous tile's stage[] and off[] are done with */
+		if (threadIdx.x < kMaxShards) {
+			base[threadIdx.x] = meta[tile * 16 + threadIdx.x];
+			uint32_t o = 0;
+			for (int j = 0; j < (int)threadIdx.x; j++) o += meta[tile * 16 + 8 + j];
+			off[threadIdx.x] = o;
+			if (threadIdx.x == kMaxShards - 1) off[kMaxShards] = o + meta[tile * 16 + 8 + threadIdx.x];
+		}
+		__syncthreads();
+		for (uint32_t q = threadIdx.x; q < tile_n; q += 256) {
+			const int dd = run_of(off, q);
+			stage[q] = ld_u2_sys(src_s[dd] + base[dd] + q - off[dd]);
+		}
+		__syncthreads();
+		for (uint32_t k = threadIdx.x; k < tile_n; k += 256)
+			gh::st_stream_u2(out + t0 + k, stage[pos[t0 + k]]);
+	}
+}
+
 int fill_ptrs(Ptrs &P, const void *const *src, int G)
 {
 	if (G < 1 || G > kMaxShards || !src) return -1;
 	for (int k = 0; k < kMaxShards; k++) P.p[k] = k < G ? (void *)src[k] : nullptr;
 	return 0;
+}
+
+/* launch-shape knobs of the routed path, read once from the environment (experiments; defaults are what bench.py runs) */
+int env_int(const char *name, int dflt)
+{
+	const char *e = getenv(name);
+	if (!e || !*e) return dflt;
+	int v = atoi(e);
+	return v > 0 ? v : dflt;
+}
+int serve_staged(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("GPUHASH_SERVE_STAGED"); v = (e && e[0] == '0') ? 0 : 1; }
+	return v;
 }
 
 unsigned grid_for(size_t n, int per_sm)
@@ -430,7 +578,7 @@ extern "C" int gpuhash_route_gather(const void *const *staged_ptrs, const uint32
 	if (fill_ptrs(S, staged_ptrs, G) || !perm_d || !counts_d || (n && !out_d)) return -1;
 	if (wait_seq && (!flags_d || !err_d)) return -1;
 	if (n == 0 && !wait_seq) return 0;                       /* with a flag wait the (empty) kernel still orders the stream */
-	route_gather_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(S, perm_d, counts_d, cap, G, (uint2 *)out_d, flags_d, wait_seq, err_d);
+	route_gather_kernel<<<grid_for(n, env_int("GPUHASH_GATHER_CTAS_PER_SM", 8)), 256, 0, (cudaStream_t)stream>>>(S, perm_d, counts_d, cap, G, (uint2 *)out_d, flags_d, wait_seq, err_d);
 	return (int)cudaGetLastError();
 }
 
@@ -583,6 +731,113 @@ serve_search_quad_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G
 	}
 }
 
+/* serve, op 0, staged: the four-lane probe of serve_search_quad_kernel with the inbox read and the result written in
+ * 64-request tiles by bulk copies (see search_quad_staged_kernel): one elected thread pulls the next tile of an inbox
+ * region into shared memory while this one is probed, and the 64 results leave as ONE 512 B bulk store into the origin's
+ * staging area -- over NVLink when the origin is a peer, where 512 B transactions instead of 32 B ones matter.
+ * Persistent CTAs (grid <= 8 per SM, tunable) walk the tiles of all G regions; a region's last, partial tile is done
+ * with plain loads/stores.  Before the last CTA raises the result flags every CTA waits for its bulk stores to be
+ * complete (not only read out) and orders them before the ticket. */
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+serve_search_staged_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, Ptrs seg_out,
+		const uint32_t *req_flags, uint32_t *err, PubArgs pub)
+{
+	__shared__ __align__(128) uint2 q_s[2][gh::kTileReq];
+	__shared__ __align__(128) uint2 o_s[2][gh::kTileReq];
+	__shared__ __align__(8) unsigned long long bar[2];
+	__shared__ uint32_t tprefix[kMaxShards + 1], count[kMaxShards];
+	__shared__ const uint2 *in_p[kMaxShards];
+	__shared__ uint2 *out_p[kMaxShards];
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = 1;
+		if (req_flags) for (int s = 0; s < G && ok; s++) ok = wait_flag(req_flags + s, pub.seq, 2000000000ULL, err);
+		uint32_t acc = 0;
+		for (int s = 0; s < G; s++) {
+			const uint32_t c = ((const volatile uint32_t *)seg_count)[s];
+			tprefix[s] = acc; count[s] = c; acc += (c + gh::kTileReq - 1) / gh::kTileReq;
+		}
+		tprefix[G] = acc;
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gh::smem_u32(&bar[0])));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gh::smem_u32(&bar[1])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (threadIdx.x < kMaxShards) {
+		in_p[threadIdx.x] = (const uint2 *)seg_in.p[threadIdx.x];
+		out_p[threadIdx.x] = (uint2 *)seg_out.p[threadIdx.x];
+	}
+	__syncthreads();
+	bool store_pending = false;                                       /* thread 0 only */
+	if (ok) {
+		const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
+		const unsigned quad = threadIdx.x >> 2;
+		const uint32_t tiles = tprefix[G];
+		/* (region, first request, full?) of tile t; `s` only moves forward */
+		auto locate = [&](uint32_t t, int &s, uint32_t &j0, bool &full) {
+			while (t >= tprefix[s + 1]) s++;
+			j0 = (t - tprefix[s]) * gh::kTileReq;
+			full = j0 + gh::kTileReq <= count[s];
+		};
+		auto issue_load = [&](int s, uint32_t j0, int stage) {
+			const uint32_t b = gh::smem_u32(&bar[stage]);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(gh::kTileReq * 8) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(gh::smem_u32(&q_s[stage][0])), "l"(in_p[s] + j0), "r"(gh::kTileReq * 8), "r"(b) : "memory");
+		};
+		uint32_t t = blockIdx.x, it = 0, phases = 0;
+		int s = 0, sn = 0;
+		uint32_t j0 = 0, jn = 0; bool full = false, fulln = false;
+		if (t < tiles) {
+			locate(t, s, j0, full);
+			if (threadIdx.x == 0 && full) issue_load(s, j0, 0);
+		}
+		sn = s;
+		for (; t < tiles; t += gridDim.x, it++) {
+			const int stage = (int)(it & 1u);
+			const uint32_t tn = t + gridDim.x;
+			if (tn < tiles) {
+				locate(tn, sn, jn, fulln);
+				if (threadIdx.x == 0 && fulln) issue_load(sn, jn, stage ^ 1);
+			}
+			const uint32_t j = j0 + quad;
+			const bool live = j < count[s];
+			uint2 q = make_uint2(0u, 0u);
+			if (full) {                                                  /* parity per stage: partial tiles do not use the barrier */
+				gh::mbar_wait(gh::smem_u32(&bar[stage]), (phases >> stage) & 1u);
+				phases ^= 1u << stage;
+				q = q_s[stage][quad];
+			} else if (live) {
+				q = ld_u2_sys(in_p[s] + j);
+			}
+			uint32_t h1, h2;
+			const uint2 o = gh::quad_probe<kPairs>(table, g, q, live, sub, grp0, half, h1, h2);
+			if (live && sub == 0) {
+				if (full) o_s[stage][quad] = o; else out_p[s][j] = o;
+			}
+			if (full) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			if (threadIdx.x == 0 && store_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+			__syncthreads();
+			if (threadIdx.x == 0 && full) {
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+					:: "l"(out_p[s] + j0), "r"(gh::smem_u32(&o_s[stage][0])), "r"(gh::kTileReq * 8) : "memory");
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+				store_pending = true;
+			}
+			s = sn; j0 = jn; full = fulln;
+		}
+	}
+	if (threadIdx.x == 0 && store_pending) {
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       /* complete, not just read out: the flag follows */
+		asm volatile("fence.proxy.async;" ::: "memory");
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G)
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[threadIdx.x] + pub.my_rank), "r"(pub.seq) : "memory");
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
 static int fill_pub(PubArgs &P, int G, int my_rank, const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs,
 		uint32_t *ticket_d, uint32_t seq)
 {
@@ -607,18 +862,64 @@ extern "C" int gpuhash_route_scatter_pub(const void *in_d, size_t n, int elem_wo
 	if (shift < 0) return -1;
 	cudaStream_t s = (cudaStream_t)stream;
 	if (n <= ((size_t)1 << 17)) {                     /* small batch: one request per thread, as many CTAs as possible */
-		const unsigned blocks = grid_for(n ? n : 1, 16);
+		const unsigned blocks = grid_for(n ? n : 1, env_int("GPUHASH_SCATTER_CTAS_PER_SM", 16));
 		if (elem_words == 2)
 			route_scatter_pub_kernel<2, 1><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
 		else
 			route_scatter_pub_kernel<3, 1><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
 	} else {
-		const unsigned blocks = grid_for((n + 3) / 4, 16);
+		const unsigned blocks = grid_for((n + 3) / 4, env_int("GPUHASH_SCATTER_CTAS_PER_SM", 16));
 		if (elem_words == 2)
 			route_scatter_pub_kernel<2, 4><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
 		else
 			route_scatter_pub_kernel<3, 4><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, perm_d, cap, P, ack_flags_d, err_d);
 	}
+	return (int)cudaGetLastError();
+}
+
+/* tile-sorted scatter + publish (map_d = NULL for insert/delete batches) and its gather; see kRouteTile above */
+extern "C" size_t gpuhash_route_map_bytes(size_t cap)
+{
+	const size_t tiles = (cap + kRouteTile - 1) / kRouteTile;
+	return tiles * kRouteTile * sizeof(uint16_t) + tiles * 16 * sizeof(uint32_t);
+}
+
+extern "C" int gpuhash_route_scatter_tiles(const void *in_d, size_t n, int elem_words, uint32_t hash_mask_total, int log2_shards,
+		const void *const *dst_ptrs, uint32_t *counts2_d, void *map_d, size_t cap, int my_rank,
+		const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs, uint32_t *ticket_d, uint32_t seq, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs D; PubArgs P;
+	if (log2_shards < 0 || log2_shards > 3 || (elem_words != 2 && elem_words != 3) || fill_ptrs(D, dst_ptrs, G) || !counts2_d
+			|| n > cap || (n && !in_d) || !peer_count_ptrs || fill_pub(P, G, my_rank, peer_count_ptrs, peer_flag_ptrs, ticket_d, seq)) return -1;
+	int bits = 0; while ((hash_mask_total >> bits) & 1u) bits++;
+	const int shift = bits - log2_shards;
+	if (shift < 0) return -1;
+	const size_t cap_tiles = (cap + kRouteTile - 1) / kRouteTile;
+	uint16_t *pos = (uint16_t *)map_d;
+	uint32_t *meta = map_d ? (uint32_t *)((char *)map_d + cap_tiles * kRouteTile * sizeof(uint16_t)) : nullptr;
+	size_t tiles = (n + kRouteTile - 1) / kRouteTile;
+	const unsigned blocks = grid_for((tiles ? tiles : 1) * 256, env_int("GPUHASH_SCATTER_CTAS_PER_SM", 8));
+	cudaStream_t s = (cudaStream_t)stream;
+	if (elem_words == 2)
+		route_scatter_tiles_kernel<2><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, pos, meta, P);
+	else
+		route_scatter_tiles_kernel<3><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, pos, meta, P);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int gpuhash_route_gather_tiles(const void *const *staged_ptrs, const void *map_d, size_t cap, int log2_shards,
+		void *out_d, size_t n, void *stream)
+{
+	const int G = 1 << log2_shards;
+	Ptrs S;
+	if (log2_shards < 0 || log2_shards > 3 || fill_ptrs(S, staged_ptrs, G) || !map_d || n > cap || (n && !out_d)) return -1;
+	if (n == 0) return 0;
+	const size_t cap_tiles = (cap + kRouteTile - 1) / kRouteTile;
+	const uint16_t *pos = (const uint16_t *)map_d;
+	const uint32_t *meta = (const uint32_t *)((const char *)map_d + cap_tiles * kRouteTile * sizeof(uint16_t));
+	const size_t tiles = (n + kRouteTile - 1) / kRouteTile;
+	route_gather_tiles_kernel<<<grid_for(tiles * 256, env_int("GPUHASH_GATHER_CTAS_PER_SM", 8)), 256, 0, (cudaStream_t)stream>>>(S, pos, meta, (uint2 *)out_d, n);
 	return (int)cudaGetLastError();
 }
 
@@ -640,9 +941,16 @@ extern "C" int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int
 	const bool pairs = gg.layout == gh::kLayoutPairs;
 #define GH_SERVE(P_, OP_) serve_kernel<P_, OP_><<<blocks, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P, st)
 	if (op == 0) {
-		const unsigned qb = grid_for((max_total ? max_total : 1) * 4, 16);
-		if (pairs) serve_search_quad_kernel<true><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
-		else       serve_search_quad_kernel<false><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
+		if (serve_staged()) {
+			/* one tile of 64 requests per CTA and iteration; G partial tiles at most on top of max_total / 64 */
+			const unsigned qb = grid_for(((max_total ? max_total : 1) + 63) / 64 * 256 + (size_t)G * 256, env_int("GPUHASH_SERVE_CTAS_PER_SM", 4));
+			if (pairs) serve_search_staged_kernel<true><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
+			else       serve_search_staged_kernel<false><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
+		} else {
+			const unsigned qb = grid_for((max_total ? max_total : 1) * 4, env_int("GPUHASH_SERVE_CTAS_PER_SM", 16));
+			if (pairs) serve_search_quad_kernel<true><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
+			else       serve_search_quad_kernel<false><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);
+		}
 	}
 	else if (op == 1) { if (pairs) GH_SERVE(true, 1); else GH_SERVE(false, 1); }
 	else              { if (pairs) GH_SERVE(true, 2); else GH_SERVE(false, 2); }

@@ -19,6 +19,7 @@ The device work sits behind a small backend object so that the choreography belo
 a stand-in backend (tests only).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -117,7 +118,10 @@ class CudaShardBackend:
         i32 = torch.int32
         self.send = torch.empty((self.G, self.cap, 3), dtype=i32, device=self.dev)      # widest element
         self.counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
-        self.perm = torch.empty((self.G, self.cap), dtype=i32, device=self.dev)
+        # collective path: perm[d][slot] = request index; fused path: the tile map of gpuhash_route_scatter_tiles
+        self.route_tiles = os.environ.get("GPUHASH_ROUTE_TILES", "1") != "0"
+        perm_words = max(self.G * self.cap, (self.L.gpuhash_route_map_bytes(self.cap) + 3) // 4)
+        self.perm = torch.empty(perm_words, dtype=i32, device=self.dev)
         self.seg_counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
         self.seg_ptrs_d = torch.zeros(MAX_SHARDS, dtype=torch.int64, device=self.dev)    # device array of region pointers
         self.p2p = None
@@ -251,6 +255,13 @@ class CudaShardBackend:
         ix.seq += 1
         if ix.seq > 1:
             self._wait(self.off_resf, ix.seq - 1)
+        if self.route_tiles:                                         # runs sorted in shared memory, written contiguously
+            N.check(L.gpuhash_route_scatter_tiles(req.data_ptr() if req.shape[0] else None, req.shape[0], words,
+                                                  self.plan.hash_mask_total, self.plan.log2, self.pp_peer_inbox, A + self.off_cnt2,
+                                                  self.perm.data_ptr() if want_perm else None, self.cap, self.rank,
+                                                  self.pp_peer_cnt, self.pp_peer_reqf, A + self.off_ticket, ix.seq,
+                                                  self._stream()), "gpuhash_route_scatter_tiles")
+            return
         N.check(L.gpuhash_route_scatter_pub(req.data_ptr() if req.shape[0] else None, req.shape[0], words,
                                             self.plan.hash_mask_total, self.plan.log2, self.pp_peer_inbox, A + self.off_cnt2,
                                             self.perm.data_ptr() if want_perm else None, self.cap, self.rank,
@@ -278,6 +289,10 @@ class CudaShardBackend:
     def _p2p_gather(self, ix, n, out):
         L, N, A = self.L, self.N, self.arena.ptr
         self._wait(self.off_resf, ix.seq)
+        if self.route_tiles:
+            N.check(L.gpuhash_route_gather_tiles(self.pp_my_stage, self.perm.data_ptr(), self.cap, self.plan.log2,
+                                                 out.data_ptr() if n else None, n, self._stream()), "gpuhash_route_gather_tiles")
+            return
         N.check(L.gpuhash_route_gather(self.pp_my_stage, self.perm.data_ptr(), A + self.off_cnt2 + 32 * (ix.seq & 1), self.cap,
                                        self.plan.log2, out.data_ptr() if n else None, n, None, 0, None, self._stream()),
                 "gpuhash_route_gather")

@@ -143,9 +143,7 @@ def main(args, rank, world, local_rank, log):
             ev[0].record()
             be_l._p2p_scatter(lane, sq, 2, True); ev[1].record()
             be_l._p2p_serve(lane, 0, 2 * sq.shape[0]); ev[2].record()
-            be_l._wait(be_l.off_resf, lane.seq)
-            N.check(L.gpuhash_route_gather(be_l.pp_my_stage, be_l.perm.data_ptr(), A + be_l.off_cnt2 + 32 * (lane.seq & 1), be_l.cap,
-                                           plan.log2, oq.data_ptr(), oq.shape[0], None, 0, None, be_l._stream())); ev[3].record()
+            be_l._p2p_gather(lane, oq.shape[0], oq); ev[3].record()
             be_l._p2p_scatter(lane, iq, 3, False); ev[4].record()
             be_l._p2p_serve(lane, 1, 2 * iq.shape[0]); ev[5].record()
             torch.cuda.synchronize()

@@ -141,3 +141,38 @@ def test_virtual_shards_on_one_gpu(gpu, world, layout):
         t = mk.DeviceTable.__new__(mk.DeviceTable); t.geom, t.ptr, t.nbytes = b.geom, b.table.ptr, b.table.nbytes
         parts.append(t.dump_reference()); t.ptr = None
     assert ref.digest(table=np.concatenate(parts)) == ref.digest()
+
+
+def test_virtual_shards_many_tiles_per_cta(gpu):
+    """Exchanges large enough that every persistent CTA of the staged serve kernel walks several 64-request tiles,
+    including the partial tile that ends a region in the middle of its walk (its barrier parity is per stage, not per
+    iteration), and that scatter/gather stride their grids: 2 ranks x 300 001 searches, three times over."""
+    import torch
+    import megakv_b200 as mk
+    from megakv_b200.sharded import ShardPlan, LocalCluster
+    from oracle import pyoracle as po
+    from tests import helpers as H
+    mk.lib().gpuhash_set_device(0); torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    world, mem_p, n = 2, 26, 300001
+    plan = ShardPlan(mem_p, world)
+    cl = LocalCluster(plan, cap=1 << 19)
+    rng = np.random.default_rng(99)
+    allk = H.random_requests(rng, world * n)
+    ref = po.Oracle(mem_p); ref.insert(allk)
+
+    def t3(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint32).reshape(-1, 3).view(np.int32).copy()).to(dev)
+
+    def t2(a):
+        return torch.from_numpy(np.ascontiguousarray(H.to_sel(a)).view(np.uint32).reshape(-1, 2).view(np.int32).copy()).to(dev)
+
+    cl.insert([t3(allk[r * n:(r + 1) * n]) for r in range(world)])
+    for rep in range(3):
+        probes = [np.concatenate([allk[rng.integers(0, world * n, n - 5000)], H.random_requests(rng, 5000 - 37 * r)]) for r in range(world)]
+        outs = cl.search([t2(p) for p in probes])
+        for r in range(world):
+            got = outs[r].cpu().numpy().view(np.uint32)
+            want = ref.search(H.to_sel(probes[r])).reshape(-1, 2)
+            assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"search mismatch rank {r} rep {rep}"
+    assert cl.error() == 0

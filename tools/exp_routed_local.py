@@ -41,8 +41,6 @@ def main():
     for _ in range(S - 1):
         lanes.append(LocalCluster(plan, cap=GROUP * BATCH, tables=lanes[0].tables))
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    cur = torch.cuda.current_stream()
-
     def stream_ptr():
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -87,6 +85,7 @@ def main():
 
     def fan(fn_lane, count):
         """count calls of fn_lane(k) round-robin over the S lane streams, joined into the current stream"""
+        cur = torch.cuda.current_stream()                          # the capturing stream while a graph is being recorded
         for st in streams:
             st.wait_stream(cur)
         for c in range(count):
@@ -100,7 +99,7 @@ def main():
         if with_insert:
             lanes[k].insert(ins[k])
 
-    res = {"G": G, "lanes": S, "batches_per_exchange": GROUP, "mem_p_total": mem_p_total, "searches_per_exchange": G * n_s}
+    res = {"env": {k_: v_ for k_, v_ in os.environ.items() if k_.startswith("GPUHASH_")}, "G": G, "lanes": S, "batches_per_exchange": GROUP, "mem_p_total": mem_p_total, "searches_per_exchange": G * n_s}
     t = timed_graph(lambda: fan(lambda k: routed(k), cycles))
     res["routed_Mops"] = round(cycles * G * GROUP * BATCH / t / 1e6, 1)
     t = timed_graph(lambda: fan(lambda k: routed(k, False), cycles))
@@ -114,9 +113,14 @@ def main():
         cl = lanes[k]
         for r in range(G):
             be = cl.be[r]; cl.ix[r].seq += 1
-            N.check(L.gpuhash_route_scatter_pub(sel[k][r].data_ptr(), n_s, 2, plan.hash_mask_total, plan.log2, be.pp_peer_inbox,
-                                                be.arena.ptr + be.off_cnt2, be.perm.data_ptr(), be.cap, r, be.pp_peer_cnt, be.pp_peer_reqf,
-                                                be.arena.ptr + be.off_ticket, cl.ix[r].seq, None, None, stream_ptr()))
+            if be.route_tiles:
+                N.check(L.gpuhash_route_scatter_tiles(sel[k][r].data_ptr(), n_s, 2, plan.hash_mask_total, plan.log2, be.pp_peer_inbox,
+                                                      be.arena.ptr + be.off_cnt2, be.perm.data_ptr(), be.cap, r, be.pp_peer_cnt, be.pp_peer_reqf,
+                                                      be.arena.ptr + be.off_ticket, cl.ix[r].seq, stream_ptr()))
+            else:
+                N.check(L.gpuhash_route_scatter_pub(sel[k][r].data_ptr(), n_s, 2, plan.hash_mask_total, plan.log2, be.pp_peer_inbox,
+                                                    be.arena.ptr + be.off_cnt2, be.perm.data_ptr(), be.cap, r, be.pp_peer_cnt, be.pp_peer_reqf,
+                                                    be.arena.ptr + be.off_ticket, cl.ix[r].seq, None, None, stream_ptr()))
 
     def serve_only(k):
         cl = lanes[k]
@@ -129,9 +133,7 @@ def main():
     def gather_only(k):
         cl = lanes[k]
         for r in range(G):
-            be = cl.be[r]
-            N.check(L.gpuhash_route_gather(be.pp_my_stage, be.perm.data_ptr(), be.arena.ptr + be.off_cnt2 + 32 * (cl.ix[r].seq & 1), be.cap,
-                                           plan.log2, out[k][r].data_ptr(), n_s, None, 0, None, stream_ptr()))
+            cl.be[r]._p2p_gather(cl.ix[r], n_s, out[k][r])             # its flag wait is already satisfied
 
     # scatter-only LAST: it advances the sequence numbers without serves, after which a full exchange would wait forever
     for name, fn in (("serve", serve_only), ("gather", gather_only), ("scatter", scatter_only)):
