@@ -899,7 +899,7 @@ extern "C" int gpuhash_route_scatter_tiles(const void *in_d, size_t n, int elem_
 	uint16_t *pos = (uint16_t *)map_d;
 	uint32_t *meta = map_d ? (uint32_t *)((char *)map_d + cap_tiles * kRouteTile * sizeof(uint16_t)) : nullptr;
 	size_t tiles = (n + kRouteTile - 1) / kRouteTile;
-	const unsigned blocks = grid_for((tiles ? tiles : 1) * 256, env_int("GPUHASH_SCATTER_CTAS_PER_SM", 8));
+	const unsigned blocks = grid_for((tiles ? tiles : 1) * 256, env_int("GPUHASH_SCATTER_CTAS_PER_SM", 2));
 	cudaStream_t s = (cudaStream_t)stream;
 	if (elem_words == 2)
 		route_scatter_tiles_kernel<2><<<blocks, 256, 0, s>>>((const uint32_t *)in_d, n, hash_mask_total, shift, G, D, counts2_d, pos, meta, P);
@@ -919,7 +919,7 @@ extern "C" int gpuhash_route_gather_tiles(const void *const *staged_ptrs, const 
 	const uint16_t *pos = (const uint16_t *)map_d;
 	const uint32_t *meta = (const uint32_t *)((const char *)map_d + cap_tiles * kRouteTile * sizeof(uint16_t));
 	const size_t tiles = (n + kRouteTile - 1) / kRouteTile;
-	route_gather_tiles_kernel<<<grid_for(tiles * 256, env_int("GPUHASH_GATHER_CTAS_PER_SM", 8)), 256, 0, (cudaStream_t)stream>>>(S, pos, meta, (uint2 *)out_d, n);
+	route_gather_tiles_kernel<<<grid_for(tiles * 256, env_int("GPUHASH_GATHER_CTAS_PER_SM", 2)), 256, 0, (cudaStream_t)stream>>>(S, pos, meta, (uint2 *)out_d, n);
 	return (int)cudaGetLastError();
 }
 

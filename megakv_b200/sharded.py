@@ -116,7 +116,7 @@ class CudaShardBackend:
         # several backends ("lanes": independent buffer sets for batches in flight) may share one shard table
         self.table = table if table is not None else DeviceBuffer(self.L.gpuhash_table_bytes(C.byref(self.geom)), zero=True)
         i32 = torch.int32
-        self.send = torch.empty((self.G, self.cap, 3), dtype=i32, device=self.dev)      # widest element
+        self._send = None                                           # collective path only: allocated at first use
         self.counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
         # collective path: perm[d][slot] = request index; fused path: the tile map of gpuhash_route_scatter_tiles
         self.route_tiles = os.environ.get("GPUHASH_ROUTE_TILES", "1") != "0"
@@ -125,6 +125,12 @@ class CudaShardBackend:
         self.seg_counts = torch.zeros(MAX_SHARDS, dtype=i32, device=self.dev)
         self.seg_ptrs_d = torch.zeros(MAX_SHARDS, dtype=torch.int64, device=self.dev)    # device array of region pointers
         self.p2p = None
+
+    @property
+    def send(self):
+        if self._send is None:
+            self._send = self.torch.empty((self.G, self.cap, 3), dtype=self.torch.int32, device=self.dev)   # widest element
+        return self._send
 
     # -- helpers
     def _stream(self):
@@ -335,11 +341,13 @@ class LocalCluster:
     def tables(self):
         return [b.table for b in self.be]
 
-    def search(self, sels, outs=None):
+    def search(self, sels, outs=None, after_scatter=None):
         """sels[r]: rank r's requests, int32 [n_r, 2]; returns (or fills) outs[r] int32 [n_r, 2]"""
         be, ix, G = self.be, self.ix, self.G
         for r in range(G):
             be[r]._p2p_scatter(ix[r], sels[r], 2, True)
+        if after_scatter:
+            after_scatter()
         for r in range(G):
             be[r]._p2p_serve(ix[r], 0, 2 * max(max(s.shape[0] for s in sels), 1))
         if outs is None:

@@ -27,6 +27,8 @@ N_INSERT = BATCH - N_SEARCH
 
 
 def main():
+    if os.environ.get("EXP_ARGS"):
+        sys.argv[1:] = os.environ["EXP_ARGS"].split()
     G = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     GROUP = int(sys.argv[3]) if len(sys.argv) > 3 else 16
@@ -94,14 +96,28 @@ def main():
         for st in streams:
             cur.wait_stream(st)
 
+    stagger = bool(int(os.environ.get("EXP_STAGGER", "0")))
+    started = {}
+
     def routed(k, with_insert=True):
-        lanes[k].search(sel[k], out[k])
+        """EXP_STAGGER=1: lane k's first exchange starts when lane k-1's first scatter phase is done, so the lanes do not
+        run their phases in lockstep (all serving, then all scattering, ...)"""
+        hook = None
+        if stagger and k not in started:
+            if k > 0 and (k - 1) in started:
+                torch.cuda.current_stream().wait_event(started[k - 1])
+            ev = torch.cuda.Event()
+            started[k] = ev
+            hook = lambda: ev.record(torch.cuda.current_stream())
+        lanes[k].search(sel[k], out[k], after_scatter=hook)
         if with_insert:
             lanes[k].insert(ins[k])
 
     res = {"env": {k_: v_ for k_, v_ in os.environ.items() if k_.startswith("GPUHASH_")}, "G": G, "lanes": S, "batches_per_exchange": GROUP, "mem_p_total": mem_p_total, "searches_per_exchange": G * n_s}
+    started.clear()
     t = timed_graph(lambda: fan(lambda k: routed(k), cycles))
     res["routed_Mops"] = round(cycles * G * GROUP * BATCH / t / 1e6, 1)
+    started.clear()
     t = timed_graph(lambda: fan(lambda k: routed(k, False), cycles))
     res["routed_search_only_Mops"] = round(cycles * G * n_s / t / 1e6, 1)
     chk = out[0][0].cpu().numpy()
@@ -136,7 +152,7 @@ def main():
             cl.be[r]._p2p_gather(cl.ix[r], n_s, out[k][r])             # its flag wait is already satisfied
 
     # scatter-only LAST: it advances the sequence numbers without serves, after which a full exchange would wait forever
-    for name, fn in (("serve", serve_only), ("gather", gather_only), ("scatter", scatter_only)):
+    for name, fn in (("serve", serve_only), ("gather", gather_only), ("scatter", scatter_only)) if not os.environ.get("EXP_SKIP_PARTS") else ():
         t = timed_graph(lambda: fan(fn, cycles))
         res[name + "_Mops"] = round(cycles * G * n_s / t / 1e6, 1)
         res[name + "_us_per_1M"] = round(t / (cycles * G * n_s) * 1e12, 2)
