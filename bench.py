@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--streams", type=int, default=32)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-operation bulk launches")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,15 +298,62 @@ def main():
     ms = C.c_float()
     N.check(L.gpuhash_roofline_gather(table, 1 << mem_p, 1 << 27, 0, 4, 3, C.byref(ms), None))
     sector_rate = (1 << 27) / (ms.value / 1e3)                       # 32 B sectors per second
+    traffic, traffic_src = None, None                                # DRAM bytes per launch of that kernel, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
-            "kernel": "gh::search_kernel", "peak_source": peak_src, "bytes_per_search": round(bytes_per_search, 2),
+            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": round(N_SEARCH * bytes_per_search),
+            "kernel": "gh::search_quad_staged_kernel<pairs>", "peak_source": peak_src, "bytes_per_search": round(bytes_per_search, 2),
             "launches": steps, "avg_launch_us_effective": round(t_s / steps * 1e6, 3),
             "bulk_launch": {"requests": bulk_n, "GB/s": round(bulk_gbs, 1), "Mops/s": round(bulk_mops, 1),
                             "frac": round(bulk_gbs / peak, 4)},
             "random_sector_probe": {"Gsectors/s": round(sector_rate / 1e9, 2), "GB/s": round(sector_rate * 32 / 1e9, 1),
                                     "search_frac_of_probe": round(steps * N_SEARCH * (2 + hits_per_search) / t_s / sector_rate, 4),
                                     "bulk_frac_of_probe": round(bulk_n * (2 + hits_per_search) / (res.total_ms / 1e3) / sector_rate, 4)}}
+
+    # ---- every operation on its own, uniform and zipf(0.99) keys, one bulk launch each (north star: search, insert and
+    #      delete Mops/s, absolute and against the random-access roofline).  Algorithmic sectors per op: 3.
+    ops = {}
+    if not args.no_ops:
+        from megakv_b200 import keystream as ks
+        ev_a, ev_b = L.gpuhash_event_create(), L.gpuhash_event_create()
+
+        def timed(fn):
+            N.check(L.gpuhash_device_sync())
+            N.check(L.gpuhash_event_record(ev_a, None)); N.check(fn()); N.check(L.gpuhash_event_record(ev_b, None))
+            t = C.c_float(); N.check(L.gpuhash_event_elapsed_ms(ev_a, ev_b, C.byref(t)))
+            return t.value / 1e3
+
+        n_ops = min(1 << 22, N_SEARCH * kd)
+        zn = ks.zetan(pop, 0.99)
+        req_d = mk.DeviceBuffer(12 * n_ops)
+        sel_d = mk.DeviceBuffer(8 * n_ops); res_d = mk.DeviceBuffer(8 * n_ops)
+
+        def report(name, secs):
+            ops[name] = {"Mops/s": round(n_ops / secs / 1e6, 1), "frac_of_sector_roofline": round(n_ops * 3 / secs / sector_rate, 3)}
+
+        for dist_name, theta, z in (("uniform", 0.0, 0.0), ("zipf0.99", 0.99, zn)):
+            N.check(L.gpuhash_gen_queries(sel_d.ptr, None, SEED, pop, n_ops, 4242, theta, z, None))
+            timed(lambda: L.gpuhash_search_ex(C.byref(geom), sel_d.ptr, res_d.ptr, table, n_ops, None, None))
+            report(f"search_{dist_name}", timed(lambda: L.gpuhash_search_ex(C.byref(geom), sel_d.ptr, res_d.ptr, table, n_ops, None, None)))
+        # insert: fresh uniform keys (claims), then zipf draws from the population (updates in place, hot slots contended)
+        fresh0 = pop + N_INSERT * (kd + 4 * 1024) + (1 << 26)
+        N.check(L.gpuhash_gen_inserts(req_d.ptr, None, SEED, fresh0, n_ops, None))
+        report("insert_uniform", timed(lambda: L.gpuhash_insert_flat_ex(C.byref(geom), table, req_d.ptr, n_ops, None, 0, None)))
+        report("delete_uniform", timed(lambda: L.gpuhash_delete_ex(C.byref(geom), req_d.ptr, table, n_ops, None, 0, None)))   # removes them again
+        N.check(L.gpuhash_gen_requests(req_d.ptr, SEED, pop, n_ops, 777, 0.99, zn, None))
+        report("insert_zipf0.99", timed(lambda: L.gpuhash_insert_flat_ex(C.byref(geom), table, req_d.ptr, n_ops, None, 0, None)))
+        report("delete_zipf0.99", timed(lambda: L.gpuhash_delete_ex(C.byref(geom), req_d.ptr, table, n_ops, None, 0, None)))
+        N.check(L.gpuhash_insert_flat_ex(C.byref(geom), table, req_d.ptr, n_ops, None, 0, None))   # put the deleted hot keys back
+        N.check(L.gpuhash_device_sync())
+        ops["requests_per_launch"] = n_ops
+        req_d.free(); sel_d.free(); res_d.free()
+        L.gpuhash_event_destroy(ev_a); L.gpuhash_event_destroy(ev_b)
 
     # ---- e2e: pinned host buffers through gpuhash_index_submit (H2D + D2H inside the timed region)
     ke = min(steps, 1024)
@@ -372,6 +420,7 @@ def main():
                 "path": best, "variants": variants},
         "gpu_launches": (2 if args.graph else 1) * steps,
         "roofline": roof,
+        "ops": ops,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
         "search_hit_fraction": round(hit_frac, 5),

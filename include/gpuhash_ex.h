@@ -238,6 +238,8 @@ int   gpuhash_ipc_close(void *imported_ptr);
 int gpuhash_gen_inserts(void *ielem_d, void *selem_d, uint64_t seed, uint64_t first, size_t n, void *stream);
 int gpuhash_gen_queries(void *selem_d, void *expect_loc_d, uint64_t seed, uint64_t population, size_t n,
 		uint64_t rng_seed, double theta, double zetan, void *stream);
+int gpuhash_gen_requests(void *ielem_d, uint64_t seed, uint64_t population, size_t n,
+		uint64_t rng_seed, double theta, double zetan, void *stream);   /* same draw as (sig, hash, loc) triples */
 
 /* ---- timed loops (CUDA events on the launching streams; the Python bench only orchestrates) ---- */
 typedef struct gpuhash_bench_result_s {

@@ -44,7 +44,7 @@ __global__ void gen_inserts_kernel(uint32_t *iel, uint32_t *sel, uint64_t seed, 
 /* theta == 0: uniform index in [0, population).  0 < theta < 1: Zipf rank by Gray et al. (the method of
  * src/zipf.h:137-183, exact pow), rank 0 = most popular = key 0. */
 __global__ void gen_queries_kernel(uint32_t *sel, uint32_t *expect_loc, uint64_t seed, uint64_t population,
-		size_t n, uint64_t rng_seed, double theta, double zetan)
+		size_t n, uint64_t rng_seed, double theta, double zetan, int triples)
 {
 	/* constants of Gray's method, computed on the device so the host side needs no libm
 	 * (the reference's link line has none: libgpuhash/test/Makefile:5) */
@@ -69,7 +69,8 @@ __global__ void gen_queries_kernel(uint32_t *sel, uint32_t *expect_loc, uint64_t
 			if (idx >= population) idx = population - 1;
 		}
 		uint32_t sig, hash; key_to_req(key_at(seed, idx), sig, hash);
-		sel[2 * i] = sig; sel[2 * i + 1] = hash;
+		if (triples) { sel[3 * i] = sig; sel[3 * i + 1] = hash; sel[3 * i + 2] = (uint32_t)(idx + 1); }
+		else { sel[2 * i] = sig; sel[2 * i + 1] = hash; }
 		if (expect_loc) expect_loc[i] = (uint32_t)(idx + 1);
 	}
 }
@@ -91,6 +92,19 @@ extern "C" int gpuhash_gen_queries(void *selem_d, void *expect_loc_d, uint64_t s
 	if (!selem_d || population < 2 || theta < 0.0 || theta >= 1.0) return -1;
 	size_t blocks = (n + 255) / 256; if (blocks > 148 * 32) blocks = 148 * 32;
 	gen_queries_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t *)selem_d, (uint32_t *)expect_loc_d,
-			seed, population, n, rng_seed, theta, zetan);
+			seed, population, n, rng_seed, theta, zetan, 0);
+	return (int)cudaGetLastError();
+}
+
+/* the same draw as gpuhash_gen_queries, emitted as (sig, hash, loc = key index + 1) triples: insert / delete requests
+ * for keys of the population (uniform or Zipf) -- updates of present keys, deletes that repeat hot keys */
+extern "C" int gpuhash_gen_requests(void *ielem_d, uint64_t seed, uint64_t population, size_t n,
+		uint64_t rng_seed, double theta, double zetan, void *stream)
+{
+	if (n == 0) return 0;
+	if (!ielem_d || population < 2 || theta < 0.0 || theta >= 1.0) return -1;
+	size_t blocks = (n + 255) / 256; if (blocks > 148 * 32) blocks = 148 * 32;
+	gen_queries_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t *)ielem_d, nullptr,
+			seed, population, n, rng_seed, theta, zetan, 1);
 	return (int)cudaGetLastError();
 }
