@@ -71,6 +71,8 @@ typedef struct gpuhash_tune_s {
 	int search_qpt;          /* 0 = choose (default); -4 = four lanes per request, one L2 request per bucket;
 	                            -5 = the same with the request/result batches staged through shared memory by
 	                                 512 B bulk copies (what 0 chooses for the pair layout and for tables beyond L2);
+	                            -6 = four lanes per request, every warp on its own: 512 B tile in by one vector access,
+	                                 four table loads per lane in flight, 512 B tile out (no shared memory, no barrier);
 	                            1, 2, 4 = one thread per request, that many requests per thread;
 	                            -1 = 4 lanes x 128-bit loads (reference layout only; comparison kernel) */
 	int search_split_mode;   /* REFERENCE layout only: 0 = by table size, 1 = location word on hit only, 2 = whole buckets */
@@ -164,6 +166,27 @@ int gpuhash_index_submit(gpuhash_index_t *ix, int worker,
 		const void *delete_in_h, size_t n_delete,
 		const void *insert_in_h, size_t n_insert);
 int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_scheduler.c:504 */
+
+/* ---- the scheduler cycle without launches (megakv_b200/csrc/gpuhash_ring.cu; north_star (c)) ----
+ * `rings` descriptor rings of `slots` entries in pinned host memory feed ONE persistent kernel (ctas_per_sm CTAs per SM,
+ * default 4, split evenly over the rings).  gpuhash_ring_submit has the arguments of gpuhash_index_submit; the buffers
+ * must be PINNED (cudaHostAlloc / cudaHostRegister): the kernel reads the requests from them and writes the results into
+ * them itself.  It costs the host one 64-byte descriptor and no CUDA call; it returns the batch number to wait for (> 0)
+ * or a negative error, and blocks only while the ring is full.  Batches of one ring run strictly in order, each as
+ * search -> delete -> insert (the reference's per-stream order, mega_scheduler.c:392-502); rings are unordered against
+ * each other.  The kernel parks itself after idle_ms without a doorbell (default 2000) and is relaunched on demand.
+ * One ring object per device at a time. */
+typedef struct gpuhash_ring_s gpuhash_ring_t;
+gpuhash_ring_t *gpuhash_ring_create(const gpuhash_geom_t *g, void *table_d, int rings, int slots, int ctas_per_sm, unsigned idle_ms);
+long long gpuhash_ring_submit(gpuhash_ring_t *q, int ring,
+		const void *search_in_h, size_t n_search, void *search_out_h,
+		const void *delete_in_h, size_t n_delete, const void *insert_in_h, size_t n_insert);
+int  gpuhash_ring_wait(gpuhash_ring_t *q, int ring, long long ticket, unsigned timeout_ms);   /* 0 ok, -2 timeout */
+int  gpuhash_ring_drain(gpuhash_ring_t *q, unsigned timeout_ms);                               /* every ring, everything submitted */
+int  gpuhash_ring_park(gpuhash_ring_t *q);                                                     /* stop the kernel (pending batches resume at the next submit) */
+void gpuhash_ring_destroy(gpuhash_ring_t *q);
+int  gpuhash_ring_ctas_per_ring(const gpuhash_ring_t *q);
+int  gpuhash_ring_trace(gpuhash_ring_t *q, int ring, unsigned long long out8[8]);   /* device timeline of the latest batch (ns) */
 
 /* ---- sharded index: routing kernels (megakv_b200/csrc/gpuhash_shard.cu; north_star (d)) ----
  * A logical table of 2^mem_p_total bytes is cut into G = 2^log2_shards contiguous bucket ranges; shard g holds
@@ -265,6 +288,11 @@ int gpuhash_bench_e2e(gpuhash_index_t *ix,
 		const void *search_h, size_t n_search, void *out_h,
 		const void *insert_h, size_t n_insert,
 		int steps, int use_graph, gpuhash_bench_result_t *res);
+
+/* The same cycles through gpuhash_ring_submit (no launches: total_ms is host wall clock, first doorbell -> last
+ * completion mark); rtt_us (optional) = median round trip of rtt_reps isolated search batches. */
+int gpuhash_bench_ring(gpuhash_ring_t *q, const void *search_h, size_t n_search, void *out_h,
+		const void *insert_h, size_t n_insert, int steps, gpuhash_bench_result_t *res, int rtt_reps, float *rtt_us);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,15 @@ SYMBOLS = {
     "gpuhash_results_publish": (_i, [_i, _i, _vp, C.c_uint32, _vp]),
     "gpuhash_route_gather": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_delete_segments": (_i, [_gp, _vp, _i, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_bench_ring": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, C.POINTER(BenchResult), _i, C.POINTER(C.c_float)]),
+    "gpuhash_ring_create": (_vp, [_vp, _vp, _i, _i, _i, C.c_uint]),
+    "gpuhash_ring_submit": (C.c_longlong, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
+    "gpuhash_ring_wait": (_i, [_vp, _i, C.c_longlong, C.c_uint]),
+    "gpuhash_ring_drain": (_i, [_vp, C.c_uint]),
+    "gpuhash_ring_park": (_i, [_vp]),
+    "gpuhash_ring_destroy": (None, [_vp]),
+    "gpuhash_ring_ctas_per_ring": (_i, [_vp]),
+    "gpuhash_ring_trace": (_i, [_vp, _i, C.POINTER(C.c_ulonglong)]),
     "gpuhash_route_map_bytes": (_sz, [_sz]),
     "gpuhash_route_scatter_tiles": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, C.c_uint32, _vp]),
     "gpuhash_route_gather_tiles": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),

@@ -711,6 +711,103 @@ __device__ __forceinline__ uint2 quad_probe(const Bucket* __restrict__ table, co
 	}
 }
 
+/* ---- a warp on its own: 64 requests in, 64 results out, no shared memory, no barrier ---- */
+
+// The warp reads its tile of 64 requests as ONE 512 B access (16 B per lane), hands the requests to its eight 4-lane
+// groups by shuffles, probes them in two blocks of four rounds (so every lane has four independent 32 B table loads in
+// flight), routes the results back so that lane l holds results 2l and 2l+1, and writes them as ONE 512 B access.
+// kSys: the batches are in pinned host memory read/written by a persistent kernel -> system-scope accesses (a weak
+// load could be served from a stale L2 line of a reused host buffer); else streaming (.cs) accesses.
+// `valid` (1..64) requests exist; in_t / out_t are 16 B aligned (out_vec false: results stored per request).
+template <bool kPairs, bool kSys>
+__device__ __forceinline__ void warp_tile_search(const Bucket* __restrict__ table, const Geom& g,
+		const uint2* in_t, uint2* out_t, uint32_t valid, bool out_vec, uint4 v /* this lane's two requests, already loaded */,
+		unsigned lane, uint32_t& hits1, uint32_t& hits2)
+{
+	const unsigned sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u, j = lane >> 2;
+	uint4 res = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+	for (int blk = 0; blk < 2; blk++) {
+		uint2 q[4]; bool live[4]; Row r[4];
+#pragma unroll
+		for (int kk = 0; kk < 4; kk++) {                         // round k: group j takes request 8k + j = lane 4k + j/2, half j&1
+			const int k = 4 * blk + kk;
+			const int src = 4 * k + (int)(j >> 1);
+			const uint32_t a = __shfl_sync(0xffffffffu, v.x, src), b = __shfl_sync(0xffffffffu, v.y, src);
+			const uint32_t c = __shfl_sync(0xffffffffu, v.z, src), d = __shfl_sync(0xffffffffu, v.w, src);
+			q[kk] = (j & 1u) ? make_uint2(c, d) : make_uint2(a, b);
+			live[kk] = (uint32_t)(8 * k) + j < valid;
+#pragma unroll
+			for (int w = 0; w < 8; w++) r[kk].w[w] = 0;
+			if (live[kk]) {
+				const uint32_t bk = sub < 2 ? bucket1(g, q[kk].y) : bucket2(g, q[kk].y, q[kk].x);
+				r[kk] = ld_row_ro(table[bk].w + 8 * half);
+			}
+		}
+#pragma unroll
+		for (int kk = 0; kk < 4; kk++) {
+			const int k = 4 * blk + kk;
+			uint2 o;
+			if (kPairs) {
+				uint32_t m = (r[kk].w[0] == q[kk].x ? 1u : 0u) | (r[kk].w[2] == q[kk].x ? 2u : 0u) | (r[kk].w[4] == q[kk].x ? 4u : 0u) | (r[kk].w[6] == q[kk].x ? 8u : 0u);
+				const uint32_t loc = (m & 1u) ? r[kk].w[1] : (m & 2u) ? r[kk].w[3] : (m & 4u) ? r[kk].w[5] : r[kk].w[7];
+				if (!live[kk]) m = 0;
+				const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
+				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));   // lowest slot wins
+				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
+				o = make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u);
+				if (sub == 0) { hits1 += (hits & 3u) ? 1u : 0u; hits2 += (hits & 12u) ? 1u : 0u; }
+			} else {
+				const uint32_t m = live[kk] ? eq_mask(r[kk], q[kk].x) : 0u;
+				const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));
+				const int l = __ffs(msig | 0x100u) - 1 & 7;
+				uint32_t loc = r[kk].w[0];
+				if (l == 1) loc = r[kk].w[1];
+				if (l == 2) loc = r[kk].w[2];
+				if (l == 3) loc = r[kk].w[3];
+				if (l == 4) loc = r[kk].w[4];
+				if (l == 5) loc = r[kk].w[5];
+				if (l == 6) loc = r[kk].w[6];
+				if (l == 7) loc = r[kk].w[7];
+				if (!msig) loc = 0;
+				o = make_uint2(__shfl_sync(0xffffffffu, loc, grp0 + 1), __shfl_sync(0xffffffffu, loc, grp0 + 3));
+				const uint32_t m2 = __shfl_sync(0xffffffffu, m, grp0 + 2);
+				if (sub == 0) { hits1 += m ? 1u : 0u; hits2 += m2 ? 1u : 0u; }
+			}
+			// results of round k belong to lanes 4k .. 4k+3: lane 4k+m takes groups 2m (first half) and 2m+1 (second half)
+			const int s0 = 8 * (int)(lane & 3u), s1 = s0 + 4;
+			const uint32_t rx = __shfl_sync(0xffffffffu, o.x, s0), ry = __shfl_sync(0xffffffffu, o.y, s0);
+			const uint32_t rz = __shfl_sync(0xffffffffu, o.x, s1), rw = __shfl_sync(0xffffffffu, o.y, s1);
+			if ((int)(lane >> 2) == k) res = make_uint4(rx, ry, rz, rw);
+		}
+	}
+	const uint32_t first = 2 * lane;                             // this lane's two results
+	if (first >= valid) return;
+	if (out_vec && first + 1 < valid) {
+		if (kSys) asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out_t + first), "r"(res.x), "r"(res.y), "r"(res.z), "r"(res.w) : "memory");
+		else      asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out_t + first), "r"(res.x), "r"(res.y), "r"(res.z), "r"(res.w) : "memory");
+	} else {
+		out_t[first] = make_uint2(res.x, res.y);
+		if (first + 1 < valid) out_t[first + 1] = make_uint2(res.z, res.w);
+	}
+}
+
+// this lane's 16 B of a tile (requests 2*lane, 2*lane + 1); partial tiles read only what exists
+template <bool kSys>
+__device__ __forceinline__ uint4 warp_tile_load(const uint2* in_t, uint32_t valid, unsigned lane)
+{
+	uint4 v = make_uint4(0u, 0u, 0u, 0u);
+	const uint32_t first = 2 * lane;
+	if (first + 1 < valid) {
+		if (kSys) asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in_t + first) : "memory");
+		else      asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in_t + first));
+	} else if (first < valid) {
+		if (kSys) asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(in_t + first) : "memory");
+		else      asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(in_t + first));
+	}
+	return v;
+}
+
 #ifdef GH_DEFINE_KERNELS
 template <bool kPairs>
 __global__ void __launch_bounds__(256)
@@ -789,6 +886,40 @@ search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		}
 	}
 	if (threadIdx.x == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Launch-path kernel built on warp_tile_search: every warp walks tiles of 64 requests on its own (grid-stride by warp),
+// the next tile's requests already in flight while this one is probed.
+template <bool kPairs>
+__global__ void __launch_bounds__(256)
+search_warp_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
+		const Bucket* __restrict__ table, size_t n, Geom g, Stats* st, unsigned head, int out_vec)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+	uint32_t h1 = 0, h2 = 0;
+	if (head && warp == 0) {                                     // the request in front of the first 16 B-aligned tile
+		const uint4 v = warp_tile_load<false>(in, 1u, lane);
+		warp_tile_search<kPairs, false>(table, g, in, out, 1u, false, v, lane, h1, h2);
+	}
+	const uint2* in_a = in + head; uint2* out_a = out + head;
+	const size_t n_a = n - head;
+	const size_t tiles = (n_a + kTileReq - 1) / kTileReq;
+	size_t t = warp;
+	uint4 v = make_uint4(0u, 0u, 0u, 0u);
+	if (t < tiles) v = warp_tile_load<false>(in_a + t * kTileReq, (uint32_t)min((size_t)kTileReq, n_a - t * kTileReq), lane);
+	for (; t < tiles; t += warps) {
+		const uint32_t valid = (uint32_t)min((size_t)kTileReq, n_a - t * kTileReq);
+		const size_t tn = t + warps;
+		uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+		if (tn < tiles) vn = warp_tile_load<false>(in_a + tn * kTileReq, (uint32_t)min((size_t)kTileReq, n_a - tn * kTileReq), lane);
+		warp_tile_search<kPairs, false>(table, g, in_a + t * kTileReq, out_a + t * kTileReq, valid, out_vec != 0, v, lane, h1, h2);
+		v = vn;
+	}
+	if (st) {
+		if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
+		if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
+	}
 }
 
 /* ---- one launch per scheduler cycle: search -> delete -> insert ---- */

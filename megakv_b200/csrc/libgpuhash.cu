@@ -75,6 +75,13 @@ static int staged_default(void)
 	if (v < 0) { const char *e = getenv("GPUHASH_SEARCH_STAGED"); v = (e && e[0] == '0') ? 0 : 1; }
 	return v;
 }
+/* GPUHASH_SEARCH_QPT=<n>: process-wide override of tune.search_qpt == 0 (A/B runs of the launch shapes) */
+static int qpt_env(void)
+{
+	static int v = 1 << 30;
+	if (v == 1 << 30) { const char *e = getenv("GPUHASH_SEARCH_QPT"); v = e && *e ? atoi(e) : 0; }
+	return v;
+}
 
 static inline gh::Geom to_geom(const gpuhash_geom_t *g)
 {
@@ -140,6 +147,7 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || (n && (!selem_d || !out_d || !table_d))) return -1;
 	if (n == 0) return 0;
 	int qpt = g_tune.search_qpt;
+	if (qpt == 0) qpt = qpt_env();
 	if (qpt == 0) {
 		/* Beyond L2 the scarce resource is L2 requests for non-resident 128 B lines (~47 G/s on B200), and the
 		 * two sectors of a bucket cost ONE request only when two lanes ask for them in the same instruction
@@ -161,6 +169,18 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 		    cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeDevice) qpt = -4;
 		(void)cudaGetLastError();
 	}
+	if (qpt == -6 && ((uintptr_t)in & 7u) == 0 && ((uintptr_t)out & 7u) == 0) {
+		/* four lanes per request, every warp on its own: 512 B tile in, four loads per lane in flight, 512 B tile out */
+		const unsigned head = ((uintptr_t)in & 15u) ? 1u : 0u;
+		const int out_vec = (((uintptr_t)out + 8u * head) & 15u) == 0;
+		size_t tiles = (n - head + gh::kTileReq - 1) / gh::kTileReq;
+		size_t blocks = (tiles + 7) / 8, cap = (size_t)sm_count_now() * 8;
+		if (blocks > cap) blocks = cap;
+		if (blocks == 0) blocks = 1;
+		if (g->layout == GPUHASH_LAYOUT_PAIRS) gh::search_warp_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
+		else                                   gh::search_warp_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
+		return (int)cudaGetLastError();
+	}
 	if (qpt == -5 && ((uintptr_t)in & 7u) == 0 && ((uintptr_t)out & 7u) == 0) {
 		/* four lanes per request, batch staged through shared memory by 512 B bulk copies (zero-copy host buffers,
 		 * fewer L2 requests for the streams).  Tiles start at the first 16 B-aligned request. */
@@ -174,7 +194,7 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 		else                                   gh::search_quad_staged_kernel<false><<<(unsigned)tiles, 256, 0, s>>>(in, out, t, n, gg, st, head, out_bulk);
 		return (int)cudaGetLastError();
 	}
-	if (qpt == -4 || qpt == -5) {                    /* four lanes per request, one L2 request per bucket */
+	if (qpt == -4 || qpt == -5 || qpt == -6) {       /* four lanes per request, one L2 request per bucket */
 		size_t blocks = (n * 4 + 255) / 256;
 		size_t cap = (size_t)sm_count_now() * 64;
 		if (blocks > cap) blocks = cap;

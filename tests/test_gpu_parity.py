@@ -94,7 +94,7 @@ def test_search_ragged_sizes(gpu, layout, n, rng):
     assert np.array_equal(gpu_search(t, sel, prezero=False), o.search(sel))
 
 
-@pytest.mark.parametrize("qpt", [1, 2, 4, -1, -4, -5])
+@pytest.mark.parametrize("qpt", [1, 2, 4, -1, -4, -5, -6])
 @pytest.mark.parametrize("split_mode", [1, 2])
 def test_search_every_launch_variant(gpu, layout, qpt, split_mode, rng):
     o = po.Oracle(20)
@@ -110,10 +110,12 @@ def test_search_every_launch_variant(gpu, layout, qpt, split_mode, rng):
         N.lib().gpuhash_set_tuning(old)
 
 
+@pytest.mark.parametrize("qpt", [-5, -6], ids=["staged", "warp"])
 @pytest.mark.parametrize("in_off,out_off", [(0, 0), (1, 1), (1, 0), (0, 1)])
 @pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 128, 129, 4097, 62259, 300001])
-def test_search_staged_kernel_alignment_and_tails(gpu, layout, n, in_off, out_off, rng):
-    """search_quad_staged_kernel moves the batch in 512 B bulk copies, which need 16 B-aligned tiles: request and
+def test_search_staged_kernel_alignment_and_tails(gpu, layout, n, in_off, out_off, qpt, rng):
+    """search_quad_staged_kernel moves the batch in 512 B bulk copies and search_warp_kernel in 512 B vector accesses
+    per warp; both need 16 B-aligned tiles: request and
     result arrays that start on an odd 8 B boundary (every second batch of bench.py does: 62259 * 8 is not a multiple
     of 16), a lone head request, partial last tiles, more tiles than CTAs -- all bit-exact against the oracle, and
     nothing outside out[0 .. 2n) is written."""
@@ -128,7 +130,7 @@ def test_search_staged_kernel_alignment_and_tails(gpu, layout, n, in_off, out_of
     out_d.upload(np.full(2 * (n + 4), 0xDEADBEEF, dtype=np.uint32))
     old = N.Tune(); N.lib().gpuhash_get_tuning(old)
     try:
-        N.lib().gpuhash_set_tuning(N.Tune(-5, 0, 4))
+        N.lib().gpuhash_set_tuning(N.Tune(qpt, 0, 4))
         N.check(N.lib().gpuhash_search_ex(C.byref(t.geom), in_d.ptr + 8 * in_off, out_d.ptr + 8 * out_off, t.ptr, n, None, None))
         mk.device_sync()
     finally:
