@@ -70,9 +70,10 @@ void   gpuhash_get_default_geom(gpuhash_geom_t *g);
 typedef struct gpuhash_tune_s {
 	int search_qpt;          /* 0 = choose (default); -4 = four lanes per request, one L2 request per bucket;
 	                            -5 = the same with the request/result batches staged through shared memory by
-	                                 512 B bulk copies (what 0 chooses for the pair layout and for tables beyond L2);
+	                                 512 B bulk copies (TMA 1-D, mbarrier);
 	                            -6 = four lanes per request, every warp on its own: 512 B tile in by one vector access,
-	                                 four table loads per lane in flight, 512 B tile out (no shared memory, no barrier);
+	                                 four table loads per lane in flight, 512 B tile out (no shared memory, no barrier)
+	                                 -- what 0 chooses for the pair layout and for tables beyond L2;
 	                            1, 2, 4 = one thread per request, that many requests per thread;
 	                            -1 = 4 lanes x 128-bit loads (reference layout only; comparison kernel) */
 	int search_split_mode;   /* REFERENCE layout only: 0 = by table size, 1 = location word on hit only, 2 = whole buckets */

@@ -154,16 +154,17 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 		 * (profiles/r01_l2_requests.md): four lanes per request.  The pair layout needs whole buckets anyway,
 		 * so it always takes that shape.  The reference layout on an L2-resident table is cheapest with one
 		 * thread per request reading the signature rows and, on a hit only, the location word. */
-		if (g->layout == GPUHASH_LAYOUT_PAIRS || gpuhash_table_bytes(g) > l2_bytes_now()) qpt = staged_default() ? -5 : -4;
+		if (g->layout == GPUHASH_LAYOUT_PAIRS || gpuhash_table_bytes(g) > l2_bytes_now()) qpt = staged_default() ? -6 : -4;
 		else qpt = n <= (size_t)sm_count_now() * 2048 ? 1 : 2;
 	}
 	const uint2 *in = (const uint2 *)selem_d; uint2 *out = (uint2 *)out_d;
 	const gh::Bucket *t = (const gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Geom gg = to_geom(g);
-	if (qpt == -5 && g_tune.search_qpt == 0 && n >= ((size_t)1 << 20)) {
-		/* Chosen by default, not asked for: one launch over a very large DEVICE-resident batch runs ~10 % faster without
-		 * the per-tile barrier (19.9 vs 17.7 Gops/s at 2^24 requests); batches in pinned host memory always stage. */
+	if ((qpt == -5 || qpt == -6) && g_tune.search_qpt == 0 && qpt_env() == 0 && n >= ((size_t)1 << 20)) {
+		/* Chosen by default, not asked for: one launch over a very large DEVICE-resident batch runs ~10 % faster with the
+		 * plain four-lane kernel and 64 CTAs per SM (19.9 vs 17.7-17.9 Gops/s at 2^24 requests); batches in pinned host
+		 * memory always go tile-wise (512 B transactions over the host link). */
 		cudaPointerAttributes pa;
 		if (cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
 		    cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeDevice) qpt = -4;
