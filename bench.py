@@ -40,6 +40,25 @@ N_INSERT = BATCH - N_SEARCH  # 3277 = 5 %
 SEED = 1
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries print to stdout (NCCL: "NCCL version ..."); the contract is ONE JSON line there.  Everything written to
+    fd 1 from now on goes to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -162,7 +181,7 @@ def run_reference_arm(args, log):
         "e2e": {"value": round(val, 3), "unit": "Mops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(mem_p, args, note=None):
@@ -199,6 +218,7 @@ def main():
         if args.verbose or os.environ.get("BENCH_VERBOSE"):
             print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
 
+    quiet_stdout()
     if args.impl == "reference":
         if rank == 0:
             run_reference_arm(args, log)
@@ -466,7 +486,7 @@ def main():
         "clocks": sampler.summary(),
         "search_hit_fraction": round(hit_frac, 5),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     L.gpuhash_host_free(hs); L.gpuhash_host_free(ho); L.gpuhash_host_free(hi)
     L.gpuhash_index_destroy(ix)
     return 0

@@ -172,8 +172,8 @@ def main(args, rank, world, local_rank, log):
 
     if quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "lanes": S, "group": GROUP, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
-                              "us_per_step": round(t_val / steps * 1e6, 2)}), flush=True)
+            B.emit({"quick": True, "n_gpus": world, "lanes": S, "group": GROUP, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
+                    "us_per_step": round(t_val / steps * 1e6, 2)})
         dist.barrier(); dist.destroy_process_group()
         return 0
     with sampler:
@@ -290,7 +290,7 @@ def main(args, rank, world, local_rank, log):
             "phase_us_one_lane": phases,
             "cpu_baseline": None, "clocks": sampler.summary(), "search_hit_fraction": round(hit, 5),
         }
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     dist.barrier()
     dist.destroy_process_group()
     return 0
