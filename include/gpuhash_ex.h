@@ -87,6 +87,13 @@ void   gpuhash_get_tuning(gpuhash_tune_t *t);
 /* ---- asynchronous launches on device pointers (stream: cudaStream_t as void*, NULL = default) ---- */
 int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, void *out_d, const void *table_d,
 		size_t n, gpuhash_stats_t *stats_d, void *stream);
+/* The steps either side of the path, on the device:
+ *   search_compact  one word per request -- bucket-1 hit, else bucket-2 hit, else 0: the sender's choice
+ *                   (src/mega_send.c:411-414) made before the results cross the host link (4 B instead of 8 B per search)
+ *   fold_keys       key bytes -> selem_t (src/mega_recv.c:349-362; fold != 0: the -DSIGNATURE XOR fold) */
+int gpuhash_search_compact_ex(const gpuhash_geom_t *g, const void *selem_d, void *out32_d, const void *table_d,
+		size_t n, gpuhash_stats_t *stats_d, void *stream);
+int gpuhash_fold_keys_ex(const void *keys_d, size_t stride, unsigned nkey, int fold, size_t n, void *selem_out_d, void *stream);
 int gpuhash_insert_ex(const gpuhash_geom_t *g, void *table_d, const void *const *blk_input_d,
 		const int *blk_elem_num_d, int num_blks, gpuhash_stats_t *stats_d, unsigned flags, void *stream);
 int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, const void *ielem_d, size_t n,
@@ -158,6 +165,9 @@ int    gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset)
 int    gpuhash_index_enable_stats(gpuhash_index_t *ix, int on);
 /* on: gpuhash_index_submit's host buffers are PINNED and the kernels access them directly over PCIe (no staging copies) */
 int    gpuhash_index_set_zero_copy(gpuhash_index_t *ix, int on);
+/* on: search_out_h receives ONE word per request -- the first non-zero of the reference's {out[2i], out[2i+1]}, i.e. the
+ * sender's choice (mega_send.c:411-414) made on the device; halves the result bytes over the host link */
+int    gpuhash_index_set_compact_results(gpuhash_index_t *ix, int on);
 
 /* One scheduler cycle for one worker with HOST buffers (pinned or pageable), in the reference's order
  * search -> delete -> insert on the worker's stream (mega_scheduler.c:392-502).  Asynchronous: results

@@ -105,6 +105,7 @@ SYMBOLS = {
     "gpuhash_index_stats": (_i, [_vp, _sp, _i]),
     "gpuhash_index_enable_stats": (_i, [_vp, _i]),
     "gpuhash_index_set_zero_copy": (_i, [_vp, _i]),
+    "gpuhash_index_set_compact_results": (_i, [_vp, _i]),
     "gpuhash_index_submit": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gpuhash_index_sync": (_i, [_vp]),
     "gpuhash_route_scatter": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -114,6 +115,8 @@ SYMBOLS = {
     "gpuhash_route_gather": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
     "gpuhash_delete_segments": (_i, [_gp, _vp, _i, _vp, _vp, _sz, _vp, _vp]),
     "gpuhash_bench_ring": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, C.POINTER(BenchResult), _i, C.POINTER(C.c_float)]),
+    "gpuhash_search_compact_ex": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gpuhash_fold_keys_ex": (_i, [_vp, _sz, C.c_uint, _i, _sz, _vp, _vp]),
     "gpuhash_ring_create": (_vp, [_vp, _vp, _i, _i, _i, C.c_uint]),
     "gpuhash_ring_submit": (C.c_longlong, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gpuhash_ring_wait": (_i, [_vp, _i, C.c_longlong, C.c_uint]),

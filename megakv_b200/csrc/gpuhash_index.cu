@@ -38,6 +38,7 @@ struct gpuhash_index_s {
 	gpuhash_stats_t *stats_d;
 	int stats_on;
 	int zero_copy;       /* kernels read requests from / write results to the caller's pinned host buffers directly */
+	int compact;         /* search_out_h gets ONE word per request (the sender's choice, mega_send.c:411-414) instead of two */
 };
 
 extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
@@ -143,6 +144,9 @@ extern "C" int gpuhash_index_enable_stats(gpuhash_index_t *ix, int on) { ix->sta
  * like the reference's batch buffers, mega_recv.c:154-156,176).  The kernels then read the requests and write the
  * results over PCIe themselves: no staging copy, no copy-engine call, one launch per non-empty part of the batch. */
 extern "C" int gpuhash_index_set_zero_copy(gpuhash_index_t *ix, int on) { ix->zero_copy = on != 0; return 0; }
+/* on: gpuhash_index_submit stores n_search words into search_out_h, word i = first non-zero of the reference's
+ * {out[2i], out[2i+1]} -- the choice the sender makes (mega_send.c:411-414), made on the device: half the result bytes. */
+extern "C" int gpuhash_index_set_compact_results(gpuhash_index_t *ix, int on) { ix->compact = on != 0; return 0; }
 
 extern "C" int gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, int reset)
 {
@@ -165,6 +169,28 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 	cudaError_t e;
 	int rc;
 	gpuhash_tune_t tune; gpuhash_get_tuning(&tune);
+	if (ix->compact) {                                                         /* one result word per search; one launch per operation kind */
+		if (n_search) {
+			if (ix->zero_copy) {
+				if ((rc = gpuhash_search_compact_ex(&ix->geom, search_in_h, search_out_h, ix->table, n_search, st, s)) != 0) return rc;
+			} else {
+				if ((e = cudaMemcpyAsync(ix->search_in_d[w], search_in_h, n_search * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+				if ((rc = gpuhash_search_compact_ex(&ix->geom, ix->search_in_d[w], ix->search_out_d[w], ix->table, n_search, st, s)) != 0) return rc;
+				if ((e = cudaMemcpyAsync(search_out_h, ix->search_out_d[w], n_search * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+			}
+		}
+		if (n_delete) {
+			const void *din = delete_in_h;
+			if (!ix->zero_copy) { if ((e = cudaMemcpyAsync(ix->delete_in_d[w], delete_in_h, n_delete * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e; din = ix->delete_in_d[w]; }
+			if ((rc = gpuhash_delete_ex(&ix->geom, din, ix->table, n_delete, st, 0, s)) != 0) return rc;
+		}
+		if (n_insert) {
+			const void *iin = insert_in_h;
+			if (!ix->zero_copy) { if ((e = cudaMemcpyAsync(ix->insert_in_d[w], insert_in_h, n_insert * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e; iin = ix->insert_in_d[w]; }
+			if ((rc = gpuhash_insert_flat_ex(&ix->geom, ix->table, iin, n_insert, st, 0, s)) != 0) return rc;
+		}
+		return 0;
+	}
 	if (ix->zero_copy) {
 		if (tune.fused_cycle)
 			return gpuhash_cycle_ex(&ix->geom, ix->table, search_in_h, n_search, search_out_h, delete_in_h, n_delete,
@@ -314,7 +340,7 @@ extern "C" int gpuhash_bench_e2e(gpuhash_index_t *ix,
 		for (int k = 0; k < ix->workers; k++) cudaStreamWaitEvent(ix->stream[k], fork, 0);
 		for (int i = 0; i < steps && rc == 0; i++)
 			rc = gpuhash_index_submit(ix, i % ix->workers,
-					(const char *)search_h + (size_t)i * n_search * 8, n_search, (char *)out_h + (size_t)i * n_search * 8,
+					(const char *)search_h + (size_t)i * n_search * 8, n_search, (char *)out_h + (size_t)i * n_search * (ix->compact ? 4 : 8),
 					NULL, 0,
 					(const char *)insert_h + (size_t)i * n_insert * 12, n_insert);
 		for (int k = 0; k < ix->workers; k++) { cudaEventRecord(ev_done[k], ix->stream[k]); cudaStreamWaitEvent(main_s, ev_done[k], 0); }
@@ -340,7 +366,7 @@ extern "C" int gpuhash_bench_e2e(gpuhash_index_t *ix,
 	res->search_ops = (unsigned long long)steps * n_search;
 	res->insert_ops = (unsigned long long)steps * n_insert;
 	res->h2d_bytes = (unsigned long long)steps * (n_search * 8 + n_insert * 12);
-	res->d2h_bytes = (unsigned long long)steps * n_search * 8;
+	res->d2h_bytes = (unsigned long long)steps * n_search * (ix->compact ? 4 : 8);
 	if (rc != 0) return rc;
 	return (int)e;
 }

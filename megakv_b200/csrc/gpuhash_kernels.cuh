@@ -465,6 +465,128 @@ done:
 	if (st && g.algo == kAlgoCuckoo) atomicAdd(&st->chain_hist[c < 7 ? c : 7], 1ULL);
 }
 
+/* ---- two lanes per request (pair layout): the whole 64 B bucket is ONE L2 request ---- */
+
+// insert_one / delete_one read a bucket with two load instructions of one thread: two L2 requests for one 128 B line
+// (profiles/r01_l2_requests.md).  Here lanes 2p and 2p+1 serve one request: each loads one half of the bucket in the SAME
+// instruction (one request), the halves are exchanged by shuffles so that both lanes hold the bucket and take the same
+// decision, the even lane commits it with the 64-bit CAS and tells its partner how that went.  Same decisions, same
+// CAS discipline, same counters as insert_one / delete_one; only the loads differ.  All 32 lanes run the loop until the
+// last pair of the warp is done (the shuffles are warp-wide).
+__device__ __forceinline__ Bkt ld_bucket_pair(const Bucket* bk, bool active, unsigned h)
+{
+	Row mine, other;
+#pragma unroll
+	for (int w = 0; w < 8; w++) mine.w[w] = 0;
+	if (active) mine = ld_row_strong(bk->w + 8 * h);
+#pragma unroll
+	for (int w = 0; w < 8; w++) other.w[w] = __shfl_xor_sync(0xffffffffu, mine.w[w], 1);
+	Bkt k;
+	k.a = h ? other : mine; k.b = h ? mine : other;
+	return k;
+}
+
+__device__ __forceinline__ void insert_pair(Bucket* table, const Geom& g, bool have,
+		uint32_t sig0, uint32_t hash, uint32_t loc0, Stats* st, unsigned lane)
+{
+	const unsigned h = lane & 1u;
+	const bool count = st && h == 0;
+	bool active = have && !(sig0 == 0 && loc0 == 0);
+	if (have && !active && count) atomicAdd(&st->ins_skipped, 1ULL);        // :101-104, 259-262
+	uint32_t sig = sig0, loc = loc0;
+	const int major = (int)(sig0 & (kSlots - 1));
+	uint32_t b = bucket1(g, hash);
+	bool alt = false;
+	uint32_t c = 0;
+	int step = 0;
+	enum { kUpdate, kClaim, kGoAlt, kOverwrite, kEvict };
+	while (__any_sync(0xffffffffu, active)) {
+		Bucket* bk = table + b;
+		const Bkt k = ld_bucket_pair(bk, active, h);
+		int kind = kGoAlt, l = 0;
+		unsigned long long expect = 0, want = 0;
+		uint32_t vsig = 0, vloc = 0;
+		if (active) {
+			const uint32_t hit = sig_mask<true>(k, sig);
+			const uint32_t empty = sig_mask<true>(k, 0u);
+			if (hit) {                                                       // update in place, lowest slot
+				kind = kUpdate; l = __ffs(hit) - 1;
+				expect = ((unsigned long long)loc_at<true>(k, l) << 32) | sig;
+				want = ((unsigned long long)loc << 32) | sig;
+			} else if (empty) {                                              // claim, first empty from the major location
+				kind = kClaim; l = first_from(empty, major);
+				expect = (unsigned long long)loc_at<true>(k, l) << 32;
+				want = ((unsigned long long)loc << 32) | sig;
+			} else if (!alt) {
+				kind = kGoAlt;                                               // bucket 1 full
+			} else {                                                         // alternate bucket full
+				l = major; vsig = sig_at<true>(k, l); vloc = loc_at<true>(k, l);
+				expect = ((unsigned long long)vloc << 32) | vsig;
+				if (g.algo == kAlgo2Choice) { kind = kOverwrite; want = ((unsigned long long)vloc << 32) | sig; }
+				else                        { kind = kEvict;     want = ((unsigned long long)loc << 32) | sig; }
+			}
+		}
+		int ok = 1;
+		if (active && h == 0 && kind != kGoAlt && expect != want)
+			ok = atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) == expect;
+		ok = __shfl_sync(0xffffffffu, ok, lane & ~1u);
+		if (active) {
+			if (kind == kGoAlt) {
+				alt = true; b = bucket2(g, hash, sig);
+				if (count) atomicAdd(&st->ins_to_b2, 1ULL);
+			} else if (!ok) {
+				if (count) atomicAdd(&st->ins_cas_retry, 1ULL);
+			} else if (kind == kUpdate) {
+				if (count) atomicAdd(&st->ins_updated, 1ULL);
+				active = false;
+			} else if (kind == kClaim) {
+				if (count) atomicAdd(alt ? &st->ins_placed_b2 : &st->ins_placed_b1, 1ULL);
+				active = false;
+			} else if (kind == kOverwrite) {
+				if (count) atomicAdd(&st->ins_overwritten, 1ULL);
+				active = false;
+			} else {                                                         // kEvict
+				if (c < g.max_cuckoo) {
+					c++;
+					if (count) atomicAdd(&st->ins_displaced, 1ULL);
+					sig = vsig; loc = vloc;
+					b = bucket2(g, hash, sig);                               // request's hash, victim's sig (:334-335)
+				} else {
+					if (count) atomicAdd(&st->ins_dropped, 1ULL);
+					active = false;
+				}
+			}
+			if (active && ++step >= kMaxSteps) { if (count) atomicAdd(&st->ins_gave_up, 1ULL); active = false; }
+			if (!active && count && g.algo == kAlgoCuckoo) atomicAdd(&st->chain_hist[c < 7 ? c : 7], 1ULL);
+		}
+	}
+}
+
+__device__ __forceinline__ int delete_pair(Bucket* table, const Geom& g, bool have,
+		uint32_t sig, uint32_t hash, uint32_t loc, unsigned lane)
+{
+	const unsigned h = lane & 1u;
+	int zeroed = 0;
+#pragma unroll
+	for (int round = 0; round < 2; round++) {
+		const bool active = have && zeroed == 0;                             // bucket 2 only if nothing was zeroed in bucket 1 (:465-468)
+		Bucket* bk = table + (round == 0 ? bucket1(g, hash) : bucket2(g, hash, sig));
+		const Bkt k = ld_bucket_pair(bk, active, h);
+		int z = 0;
+		if (active && h == 0) {
+			uint32_t m = sig_mask<true>(k, sig) & loc_mask<true>(k, loc);
+			const unsigned long long expect = ((unsigned long long)loc << 32) | sig;
+			while (m) {
+				const int l = __ffs(m) - 1; m &= m - 1;
+				if (atomicCAS((unsigned long long*)&bk->w[2 * l], expect, (unsigned long long)loc << 32) == expect) z++;
+			}
+		}
+		z = __shfl_sync(0xffffffffu, z, lane & ~1u);
+		if (active) zeroed = z;
+	}
+	return zeroed;
+}
+
 #ifdef GH_DEFINE_KERNELS
 template <bool kPairs>
 __global__ void __launch_bounds__(256)
@@ -515,6 +637,36 @@ insert_segments_kernel(Bucket* table, const uint32_t* const* __restrict__ blk_in
 			const uint32_t* p = base[k] + 3 * (e - prefix[k]);
 			insert_one<kPairs>(table, g, ld_stream_u32(p), ld_stream_u32(p + 1), ld_stream_u32(p + 2), st);
 		}
+	}
+}
+
+// two lanes per request (pair layout only): warp-uniform trip count, lanes beyond n idle but take part in the shuffles
+__global__ void __launch_bounds__(256)
+insert_flat_pair_kernel(Bucket* table, const uint32_t* __restrict__ in, size_t n, Geom g, Stats* st)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const size_t per_iter = ((size_t)gridDim.x * blockDim.x) >> 1;
+	const size_t n_up = (n + 15) & ~(size_t)15;
+	for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; i < n_up; i += per_iter) {
+		const bool have = i < n;
+		uint32_t sig = 0, hash = 0, loc = 0;
+		if (have) { sig = ld_stream_u32(in + 3 * i); hash = ld_stream_u32(in + 3 * i + 1); loc = ld_stream_u32(in + 3 * i + 2); }
+		insert_pair(table, g, have, sig, hash, loc, st, lane);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+delete_pair_kernel(const uint32_t* __restrict__ in, Bucket* table, size_t n, Geom g, Stats* st)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const size_t per_iter = ((size_t)gridDim.x * blockDim.x) >> 1;
+	const size_t n_up = (n + 15) & ~(size_t)15;
+	for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; i < n_up; i += per_iter) {
+		const bool have = i < n;
+		uint32_t sig = 0, hash = 0, loc = 0;
+		if (have) { sig = ld_stream_u32(in + 3 * i); hash = ld_stream_u32(in + 3 * i + 1); loc = ld_stream_u32(in + 3 * i + 2); }
+		const int z = delete_pair(table, g, have, sig, hash, loc, lane);
+		if (st && z && (lane & 1u) == 0) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
 	}
 }
 
@@ -719,9 +871,11 @@ __device__ __forceinline__ uint2 quad_probe(const Bucket* __restrict__ table, co
 // kSys: the batches are in pinned host memory read/written by a persistent kernel -> system-scope accesses (a weak
 // load could be served from a stale L2 line of a reused host buffer); else streaming (.cs) accesses.
 // `valid` (1..64) requests exist; in_t / out_t are 16 B aligned (out_vec false: results stored per request).
-template <bool kPairs, bool kSys>
+// kCompact: one word per request instead of two -- the first non-zero of {bucket-1 hit, bucket-2 hit}, which is what the
+// consumer takes anyway (src/mega_send.c:411-414); out_t is then uint32_t[64] (8 B aligned for the vector store).
+template <bool kPairs, bool kSys, bool kCompact = false>
 __device__ __forceinline__ void warp_tile_search(const Bucket* __restrict__ table, const Geom& g,
-		const uint2* in_t, uint2* out_t, uint32_t valid, bool out_vec, uint4 v /* this lane's two requests, already loaded */,
+		const uint2* in_t, void* out_t_, uint32_t valid, bool out_vec, uint4 v /* this lane's two requests, already loaded */,
 		unsigned lane, uint32_t& hits1, uint32_t& hits2)
 {
 	const unsigned sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u, j = lane >> 2;
@@ -783,6 +937,19 @@ __device__ __forceinline__ void warp_tile_search(const Bucket* __restrict__ tabl
 	}
 	const uint32_t first = 2 * lane;                             // this lane's two results
 	if (first >= valid) return;
+	if (kCompact) {
+		uint32_t* out_c = (uint32_t*)out_t_;
+		const uint32_t c0 = res.x ? res.x : res.y, c1 = res.z ? res.z : res.w;
+		if (out_vec && first + 1 < valid) {
+			if (kSys) asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" :: "l"(out_c + first), "r"(c0), "r"(c1) : "memory");
+			else      asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(out_c + first), "r"(c0), "r"(c1) : "memory");
+		} else {
+			out_c[first] = c0;
+			if (first + 1 < valid) out_c[first + 1] = c1;
+		}
+		return;
+	}
+	uint2* out_t = (uint2*)out_t_;
 	if (out_vec && first + 1 < valid) {
 		if (kSys) asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out_t + first), "r"(res.x), "r"(res.y), "r"(res.z), "r"(res.w) : "memory");
 		else      asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out_t + first), "r"(res.x), "r"(res.y), "r"(res.z), "r"(res.w) : "memory");
@@ -890,19 +1057,21 @@ search_quad_staged_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 
 // Launch-path kernel built on warp_tile_search: every warp walks tiles of 64 requests on its own (grid-stride by warp),
 // the next tile's requests already in flight while this one is probed.
-template <bool kPairs>
+template <bool kPairs, bool kCompact = false>
 __global__ void __launch_bounds__(256)
-search_warp_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
+search_warp_kernel(const uint2* __restrict__ in, void* __restrict__ out_,
 		const Bucket* __restrict__ table, size_t n, Geom g, Stats* st, unsigned head, int out_vec)
 {
+	constexpr size_t kOutBytes = kCompact ? 4 : 8;               // per request
+	char* out = (char*)out_;
 	const unsigned lane = threadIdx.x & 31u;
 	const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
 	uint32_t h1 = 0, h2 = 0;
 	if (head && warp == 0) {                                     // the request in front of the first 16 B-aligned tile
 		const uint4 v = warp_tile_load<false>(in, 1u, lane);
-		warp_tile_search<kPairs, false>(table, g, in, out, 1u, false, v, lane, h1, h2);
+		warp_tile_search<kPairs, false, kCompact>(table, g, in, out, 1u, false, v, lane, h1, h2);
 	}
-	const uint2* in_a = in + head; uint2* out_a = out + head;
+	const uint2* in_a = in + head; char* out_a = out + kOutBytes * head;
 	const size_t n_a = n - head;
 	const size_t tiles = (n_a + kTileReq - 1) / kTileReq;
 	size_t t = warp;
@@ -913,12 +1082,44 @@ search_warp_kernel(const uint2* __restrict__ in, uint2* __restrict__ out,
 		const size_t tn = t + warps;
 		uint4 vn = make_uint4(0u, 0u, 0u, 0u);
 		if (tn < tiles) vn = warp_tile_load<false>(in_a + tn * kTileReq, (uint32_t)min((size_t)kTileReq, n_a - tn * kTileReq), lane);
-		warp_tile_search<kPairs, false>(table, g, in_a + t * kTileReq, out_a + t * kTileReq, valid, out_vec != 0, v, lane, h1, h2);
+		warp_tile_search<kPairs, false, kCompact>(table, g, in_a + t * kTileReq, out_a + kOutBytes * t * kTileReq, valid, out_vec != 0, v, lane, h1, h2);
 		v = vn;
 	}
 	if (st) {
 		if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
 		if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
+	}
+}
+
+/* ---- the step in front of the path: key bytes -> (sig, hash) ---- */
+
+// src/mega_recv.c:349-362: sig64 = first 8 key bytes; with -DSIGNATURE the remaining 8-byte words are XOR-folded into it,
+// the last, partial word masked to the bytes that belong to the key (:352-359); hash = high 32 bits, sig = low 32 bits.
+// Keys of `nkey` >= 8 bytes at keys + i * stride.  (Without SIGNATURE the request IS the first 8 key bytes -- fold = 0.)
+// One thread per key, byte loads for the tail so nothing past the key is read (the reference reads the full word and masks).
+__global__ void __launch_bounds__(256)
+fold_keys_kernel(const unsigned char* __restrict__ keys, size_t stride, uint32_t nkey, int fold, size_t n, uint2* __restrict__ out)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned char* k = keys + i * stride;
+		unsigned long long sig = 0;
+#pragma unroll
+		for (int b = 0; b < 8; b++) sig |= (unsigned long long)k[b] << (8 * b);
+		if (fold) {
+			uint32_t j = 8;
+			for (; j + 8 <= nkey; j += 8) {
+				unsigned long long w = 0;
+#pragma unroll
+				for (int b = 0; b < 8; b++) w |= (unsigned long long)k[j + b] << (8 * b);
+				sig ^= w;
+			}
+			if (j < nkey) {
+				unsigned long long w = 0;
+				for (uint32_t b = 0; j + b < nkey; b++) w |= (unsigned long long)k[j + b] << (8 * b);
+				sig ^= w;
+			}
+		}
+		out[i] = make_uint2((uint32_t)sig, (uint32_t)(sig >> 32));
 	}
 }
 

@@ -75,6 +75,14 @@ static int staged_default(void)
 	if (v < 0) { const char *e = getenv("GPUHASH_SEARCH_STAGED"); v = (e && e[0] == '0') ? 0 : 1; }
 	return v;
 }
+/* GPUHASH_UPDATE_PAIR=0: insert/delete launches keep one thread per request (A/B runs; default: two lanes per request
+ * for the pair layout, one L2 request per bucket) */
+static int update_pair_default(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("GPUHASH_UPDATE_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+	return v;
+}
 /* GPUHASH_SEARCH_QPT=<n>: process-wide override of tune.search_qpt == 0 (A/B runs of the launch shapes) */
 static int qpt_env(void)
 {
@@ -175,11 +183,17 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 		const unsigned head = ((uintptr_t)in & 15u) ? 1u : 0u;
 		const int out_vec = (((uintptr_t)out + 8u * head) & 15u) == 0;
 		size_t tiles = (n - head + gh::kTileReq - 1) / gh::kTileReq;
-		size_t blocks = (tiles + 7) / 8, cap = (size_t)sm_count_now() * 8;
+		/* a 64 K batch is 973 tiles: with 8 warps per CTA that is 122 CTAs -- fewer than SMs.  Small launches take
+		 * smaller CTAs so that a lone batch still reaches every SM; large ones 8 warps per CTA, 8 CTAs per SM. */
+		static int blk_env = -1;
+		if (blk_env < 0) { const char *e = getenv("GPUHASH_WARP_BLOCK"); blk_env = e && *e ? atoi(e) : 0; }
+		unsigned threads = blk_env ? (unsigned)blk_env : (tiles <= (size_t)sm_count_now() * 16 ? 64u : 256u);
+		const size_t wpc = threads / 32;
+		size_t blocks = (tiles + wpc - 1) / wpc, cap = (size_t)sm_count_now() * (2048 / threads);
 		if (blocks > cap) blocks = cap;
 		if (blocks == 0) blocks = 1;
-		if (g->layout == GPUHASH_LAYOUT_PAIRS) gh::search_warp_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
-		else                                   gh::search_warp_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
+		if (g->layout == GPUHASH_LAYOUT_PAIRS) gh::search_warp_kernel<true><<<(unsigned)blocks, threads, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
+		else                                   gh::search_warp_kernel<false><<<(unsigned)blocks, threads, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
 		return (int)cudaGetLastError();
 	}
 	if (qpt == -5 && ((uintptr_t)in & 7u) == 0 && ((uintptr_t)out & 7u) == 0) {
@@ -221,6 +235,42 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 	if (qpt >= 4)      launch_search<4>(mode, in, out, t, n, gg, st, s);
 	else if (qpt >= 2) launch_search<2>(mode, in, out, t, n, gg, st, s);
 	else               launch_search<1>(mode, in, out, t, n, gg, st, s);
+	return (int)cudaGetLastError();
+}
+
+/* One word per request: out32[i] = bucket-1 hit, else bucket-2 hit, else 0 -- what the sender picks out of the pair
+ * (src/mega_send.c:411-414), decided on the device so that half the result bytes cross the host link. */
+extern "C" int gpuhash_search_compact_ex(const gpuhash_geom_t *g, const void *selem_d, void *out32_d,
+		const void *table_d, size_t n, gpuhash_stats_t *stats_d, void *stream)
+{
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || (n && (!selem_d || !out32_d || !table_d))) return -1;
+	if (((uintptr_t)selem_d & 7u) || ((uintptr_t)out32_d & 3u)) return -1;
+	if (n == 0) return 0;
+	const uint2 *in = (const uint2 *)selem_d;
+	const unsigned head = ((uintptr_t)in & 15u) ? 1u : 0u;
+	const int out_vec = (((uintptr_t)out32_d + 4u * head) & 7u) == 0;
+	size_t tiles = (n - head + gh::kTileReq - 1) / gh::kTileReq;
+	size_t blocks = (tiles + 7) / 8, cap = (size_t)sm_count_now() * 8;
+	if (blocks > cap) blocks = cap;
+	if (blocks == 0) blocks = 1;
+	gh::Geom gg = to_geom(g);
+	cudaStream_t s = (cudaStream_t)stream;
+	if (g->layout == GPUHASH_LAYOUT_PAIRS)
+		gh::search_warp_kernel<true, true><<<(unsigned)blocks, 256, 0, s>>>(in, out32_d, (const gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d, head, out_vec);
+	else
+		gh::search_warp_kernel<false, true><<<(unsigned)blocks, 256, 0, s>>>(in, out32_d, (const gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d, head, out_vec);
+	return (int)cudaGetLastError();
+}
+
+/* Key bytes -> search requests (src/mega_recv.c:349-362): n keys of nkey >= 8 bytes, `stride` bytes apart; fold != 0 =
+ * the reference built with -DSIGNATURE (XOR of all 8-byte words, tail masked), fold == 0 = first 8 bytes only. */
+extern "C" int gpuhash_fold_keys_ex(const void *keys_d, size_t stride, unsigned nkey, int fold, size_t n, void *selem_out_d, void *stream)
+{
+	if (nkey < 8 || stride < nkey || (n && (!keys_d || !selem_out_d)) || ((uintptr_t)selem_out_d & 7u)) return -1;
+	if (n == 0) return 0;
+	size_t blocks = (n + 255) / 256, cap = (size_t)sm_count_now() * 16;
+	if (blocks > cap) blocks = cap;
+	gh::fold_keys_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char *)keys_d, stride, nkey, fold, n, (uint2 *)selem_out_d);
 	return (int)cudaGetLastError();
 }
 
@@ -268,6 +318,12 @@ extern "C" int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, co
 	} else {
 		size_t blocks = (n + 255) / 256;
 		size_t cap = (size_t)sm_count_now() * 32;        /* grid-stride beyond 32 CTAs per SM */
+		if (gg.layout == gh::kLayoutPairs && update_pair_default()) {
+			blocks = (2 * n + 255) / 256;
+			if (blocks > cap) blocks = cap;
+			gh::insert_flat_pair_kernel<<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+			return (int)cudaGetLastError();
+		}
 		if (blocks > cap) blocks = cap;
 		if (gg.layout == gh::kLayoutPairs)
 			gh::insert_flat_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d,
@@ -294,6 +350,12 @@ extern "C" int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, v
 	} else {
 		size_t blocks = (n + 255) / 256;
 		size_t cap = (size_t)sm_count_now() * 32;
+		if (gg.layout == gh::kLayoutPairs && update_pair_default()) {
+			blocks = (2 * n + 255) / 256;
+			if (blocks > cap) blocks = cap;
+			gh::delete_pair_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);
+			return (int)cudaGetLastError();
+		}
 		if (blocks > cap) blocks = cap;
 		if (gg.layout == gh::kLayoutPairs)
 			gh::delete_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((const uint32_t *)delem_d, (gh::Bucket *)table_d, n, gg, (gh::Stats *)stats_d);

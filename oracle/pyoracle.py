@@ -162,3 +162,34 @@ def keys(seed, first_index, n):
 
 def now():
     return lib().orc_now_sec()
+
+
+# ---- the steps either side of the path, restated for the tests ----
+
+def fold_keys(keys, fold):
+    """src/mega_recv.c:349-362.  keys: uint8 [n, nkey], nkey >= 8.  sig64 = the first 8 key bytes (little endian); with
+    the reference's -DSIGNATURE (fold=True) every further full 8-byte word is XORed in (:352-354) and the last, partial
+    word masked to the key's own bytes (:355-358).  hash = high 32 bits, sig = low 32 bits (:361-362)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint8)
+    n, nkey = keys.shape
+    assert nkey >= 8
+    sig = keys[:, :8].copy().view("<u8").reshape(n)
+    if fold:
+        i = 8
+        while i + 8 <= nkey:
+            sig = sig ^ keys[:, i:i + 8].copy().view("<u8").reshape(n)
+            i += 8
+        if i < nkey:
+            tail = np.zeros((n, 8), dtype=np.uint8)
+            tail[:, : nkey - i] = keys[:, i:]
+            sig = sig ^ tail.view("<u8").reshape(n)
+    sel = np.empty(n, dtype=SEL_DT)
+    sel["sig"] = (sig & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    sel["hash"] = (sig >> np.uint64(32)).astype(np.uint32)
+    return sel
+
+
+def compact_results(out):
+    """src/mega_send.c:411-414: the sender takes search_out[2i], and search_out[2i+1] when that is 0."""
+    o = np.asarray(out, dtype=np.uint32).reshape(-1, 2)
+    return np.where(o[:, 0] != 0, o[:, 0], o[:, 1])

@@ -576,3 +576,43 @@ def test_full_size_table_properties(gpu, layout, rng):
     hi = np.array([(0x7777, 0x0FFFFFFF, 99), (0x7778, 0xFFFFFFFF, 98)], dtype=mk.IEL_DT)
     gpu_insert(t, hi)
     assert list(gpu_search(t, H.to_sel(hi))[[0, 2]]) == [99, 98]
+
+
+# ----------------------------------------------------------------------------- the steps either side of the path
+
+@pytest.mark.parametrize("in_off,out_off", [(0, 0), (1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4097, 62259, 300001])
+def test_search_compact_is_the_senders_choice(gpu, layout, n, in_off, out_off, rng):
+    """gpuhash_search_compact_ex: one word per request = search_out[2i] if non-zero else search_out[2i+1]
+    (src/mega_send.c:411-414), including keys that sit in their alternate bucket and keys present in both."""
+    o = po.Oracle(16)
+    iel = H.random_requests(rng, 7000)                           # load 0.85: many keys in bucket 2, some orphans
+    o.insert(iel)
+    t = table_from_oracle(o, layout)
+    sel = np.concatenate([H.to_sel(iel), H.to_sel(H.random_requests(rng, 2000))])[rng.integers(0, 9000, n)]
+    in_d = mk.DeviceBuffer(8 * (n + 4)); out_d = mk.DeviceBuffer(4 * (n + 8))
+    pad = np.zeros(n + 4, dtype=mk.SEL_DT); pad[in_off:in_off + n] = sel
+    in_d.upload(pad)
+    out_d.upload(np.full(n + 8, 0xDEADBEEF, dtype=np.uint32))
+    N.check(N.lib().gpuhash_search_compact_ex(C.byref(t.geom), in_d.ptr + 8 * in_off, out_d.ptr + 4 * out_off, t.ptr, n, None, None))
+    mk.device_sync()
+    got = out_d.download(np.uint32)
+    want2 = o.search(sel)
+    assert (want2.reshape(-1, 2)[:, 0] == 0).any() or n < 64     # the case exercises bucket-2 hits
+    assert np.array_equal(got[out_off:out_off + n], po.compact_results(want2))
+    assert np.all(got[:out_off] == 0xDEADBEEF) and np.all(got[out_off + n:] == 0xDEADBEEF)
+
+
+@pytest.mark.parametrize("fold", [0, 1])
+@pytest.mark.parametrize("nkey,stride", [(8, 8), (16, 16), (20, 24), (31, 31), (128, 130)])
+def test_fold_keys_matches_receiver_derivation(gpu, nkey, stride, fold, rng):
+    """gpuhash_fold_keys_ex against the restatement of src/mega_recv.c:349-362 (plain and -DSIGNATURE builds)"""
+    n = 50001
+    raw = rng.integers(0, 256, size=(n, stride), dtype=np.uint8)
+    keys_d = mk.DeviceBuffer.from_host(raw)
+    out_d = mk.DeviceBuffer(8 * n)
+    N.check(N.lib().gpuhash_fold_keys_ex(keys_d.ptr, stride, nkey, fold, n, out_d.ptr, None))
+    mk.device_sync()
+    got = out_d.download(np.uint32).view(mk.SEL_DT)
+    want = po.fold_keys(raw[:, :nkey], bool(fold))
+    assert np.array_equal(got["sig"], want["sig"]) and np.array_equal(got["hash"], want["hash"])

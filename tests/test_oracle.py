@@ -291,3 +291,17 @@ def test_golden_vectors(name):
         if k == "case":
             continue
         assert np.array_equal(got[k], g[k]), f"{name}: {k} differs"
+
+
+def test_fold_keys_and_compact_results_restatements():
+    """src/mega_recv.c:349-362 and src/mega_send.c:411-414 on hand-computed cases"""
+    k = np.arange(20, dtype=np.uint8).reshape(1, 20)
+    w0 = int.from_bytes(bytes(range(0, 8)), "little"); w1 = int.from_bytes(bytes(range(8, 16)), "little")
+    tail = int.from_bytes(bytes(range(16, 20)), "little")
+    s = po.fold_keys(k, True)
+    assert (int(s["hash"][0]) << 32 | int(s["sig"][0])) == w0 ^ w1 ^ tail
+    s = po.fold_keys(k, False)
+    assert (int(s["hash"][0]) << 32 | int(s["sig"][0])) == w0
+    s = po.fold_keys(k[:, :8], True)
+    assert (int(s["hash"][0]) << 32 | int(s["sig"][0])) == w0
+    assert po.compact_results(np.array([5, 0, 0, 7, 0, 0, 3, 4], dtype=np.uint32)).tolist() == [5, 7, 0, 3]
