@@ -285,7 +285,8 @@ def main():
 
     # replayed as a graph, one launch per operation kind overlaps better across streams than the single-launch cycle
     # (tools/exp_mixed.py: 19.3 vs 14.1 Gops/s); issued call by call it is the other way round (11.4 vs 13.5)
-    L.gpuhash_set_tuning(C.byref(N.Tune(0, 0, 4, 0 if args.graph else 1)))
+    fused_resident = int(os.environ["BENCH_FUSED"]) if os.environ.get("BENCH_FUSED") else (0 if args.graph else 1)
+    L.gpuhash_set_tuning(C.byref(N.Tune(0, 0, 4, fused_resident)))
     sampler = ClockSampler(local_rank)
     resident(0, warm)                                               # W untimed warm-up steps
     with sampler:
@@ -404,7 +405,11 @@ def main():
     # four ways through the same host-buffer call: staging copies or zero-copy (kernels read/write the pinned host
     # buffers over PCIe themselves), each launched call by call or replayed as one CUDA graph per pass
     variants = {}
-    for zero_copy, graph, name in [(0, 0, "staged"), (0, 1, "staged+graph"), (1, 0, "zero_copy"), (1, 1, "zero_copy+graph")]:
+    tune_bench = N.Tune(); L.gpuhash_get_tuning(C.byref(tune_bench))
+    for zero_copy, graph, fused, name in [(0, 0, None, "staged"), (0, 1, None, "staged+graph"), (1, 0, None, "zero_copy"),
+                                          (1, 1, None, "zero_copy+graph"), (1, 1, 1, "zero_copy+graph+one_launch")]:
+        # one_launch: the whole cycle of a worker (searches, then inserts) is ONE kernel (gpuhash_cycle_ex)
+        L.gpuhash_set_tuning(C.byref(N.Tune(0, 0, 4, tune_bench.fused_cycle if fused is None else fused)))
         L.gpuhash_index_set_zero_copy(ix, zero_copy)
         e2e_pass(min(ke, max(3, warm)), graph)                       # warm-up
         ho_np[:] = 0
@@ -414,6 +419,7 @@ def main():
         assert ok > 0.999, f"e2e ({name}) results did not come back: {ok}"
         variants[name] = {"Mops/s": round(steps * BATCH / t_e / 1e6, 1), "ms": round(t_e * 1e3, 3), "wall_ms": round(wall * 1e3, 2)}
         log(f"e2e {name}: {steps} steps in {t_e * 1e3:.2f} ms (wall {wall * 1e3:.1f}) -> {steps * BATCH / t_e / 1e6:.1f} Mops/s")
+    L.gpuhash_set_tuning(C.byref(tune_bench))
     # the consumer only ever takes one of the two result words (mega_send.c:411-414): let the device choose and send 4 B
     # per search back instead of 8.  Reported next to the others, not as the headline: it changes what search_out holds.
     L.gpuhash_index_set_zero_copy(ix, 1); L.gpuhash_index_set_compact_results(ix, 1)
@@ -492,7 +498,7 @@ def main():
         "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": 8 * N_SEARCH + 12 * N_INSERT,
                 "d2h_bytes_per_step": 8 * N_SEARCH, "wall_ms": round(wall_e * 1e3, 2), "workers": S,
                 "path": best, "variants": variants, "ring": ring_info, "compact_results": compact_info},
-        "gpu_launches": (2 if args.graph else 1) * steps,
+        "gpu_launches": (1 if fused_resident else 2) * steps,
         "roofline": roof,
         "ops": ops,
         "cpu_baseline": cpu,

@@ -631,11 +631,26 @@ insert_segments_kernel(Bucket* table, const uint32_t* const* __restrict__ blk_in
 		__syncthreads();
 		const unsigned long long total = prefix[nseg];
 		int k = 0;
-		for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-				e < total; e += (unsigned long long)gridDim.x * blockDim.x) {
-			while (e >= prefix[k + 1]) k++;                          // e only grows
-			const uint32_t* p = base[k] + 3 * (e - prefix[k]);
-			insert_one<kPairs>(table, g, ld_stream_u32(p), ld_stream_u32(p + 1), ld_stream_u32(p + 2), st);
+		if (kPairs) {                                                // two lanes per request, warp-uniform trip count
+			const unsigned long long total_up = (total + 15ULL) & ~15ULL;
+			for (unsigned long long e = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+					e < total_up; e += ((unsigned long long)gridDim.x * blockDim.x) >> 1) {
+				const bool have = e < total;
+				uint32_t a = 0, b = 0, c = 0;
+				if (have) {
+					while (e >= prefix[k + 1]) k++;                  // e only grows
+					const uint32_t* p = base[k] + 3 * (e - prefix[k]);
+					a = ld_stream_u32(p); b = ld_stream_u32(p + 1); c = ld_stream_u32(p + 2);
+				}
+				insert_pair(table, g, have, a, b, c, st, threadIdx.x & 31u);
+			}
+		} else {
+			for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+					e < total; e += (unsigned long long)gridDim.x * blockDim.x) {
+				while (e >= prefix[k + 1]) k++;                      // e only grows
+				const uint32_t* p = base[k] + 3 * (e - prefix[k]);
+				insert_one<kPairs>(table, g, ld_stream_u32(p), ld_stream_u32(p + 1), ld_stream_u32(p + 2), st);
+			}
 		}
 	}
 }
@@ -1160,53 +1175,51 @@ cycle_kernel(Bucket* table, Geom g, Stats* st, CycleArgs a)
 {
 	const unsigned int bid = blockIdx.x;
 	int phase;
-	if (bid < a.search_ctas) {                                       // ---- search: four lanes per request
+	if (bid < a.search_ctas) {                                       // ---- search: every warp walks 64-request tiles (warp_tile_search)
 		phase = 0;
-		const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, grp0 = lane & ~3u, half = sub & 1u;
-		const unsigned long long per_iter = ((unsigned long long)a.search_ctas * blockDim.x) >> 2;
-		const unsigned long long n = a.n_search, n_up = (n + 7) & ~7ULL;
-		for (unsigned long long i = ((unsigned long long)bid * blockDim.x + threadIdx.x) >> 2; i < n_up; i += per_iter) {
-			const bool live = i < n;
-			uint2 q = make_uint2(0u, 0u);
-			Row r;
-#pragma unroll
-			for (int k = 0; k < 8; k++) r.w[k] = 0;
-			if (live) {
-				q = ld_stream_u2(a.search_in + i);
-				const uint32_t b = sub < 2 ? bucket1(g, q.y) : bucket2(g, q.y, q.x);
-				r = ld_row_ro(table[b].w + 8 * half);
-			}
-			uint32_t m, loc;
-			if (kPairs) {
-				m = (r.w[0] == q.x ? 1u : 0u) | (r.w[2] == q.x ? 2u : 0u) | (r.w[4] == q.x ? 4u : 0u) | (r.w[6] == q.x ? 8u : 0u);
-				loc = (m & 1u) ? r.w[1] : (m & 2u) ? r.w[3] : (m & 4u) ? r.w[5] : r.w[7];
-				if (!live) m = 0;
-				const unsigned hits = (__ballot_sync(0xffffffffu, m != 0) >> grp0) & 0xfu;
-				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 1u) ? 0 : 1));
-				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + ((hits & 4u) ? 2 : 3));
-				if (live && sub == 0) st_stream_u2(a.search_out + i, make_uint2((hits & 3u) ? l0 : 0u, (hits & 12u) ? l1 : 0u));
-			} else {
-				m = live ? eq_mask(r, q.x) : 0u;
-				const uint32_t msig = __shfl_sync(0xffffffffu, m, grp0 + (sub & 2u));
-				const int l = __ffs(msig | 0x100u) - 1 & 7;
-				loc = r.w[0];
-				if (l == 1) loc = r.w[1];
-				if (l == 2) loc = r.w[2];
-				if (l == 3) loc = r.w[3];
-				if (l == 4) loc = r.w[4];
-				if (l == 5) loc = r.w[5];
-				if (l == 6) loc = r.w[6];
-				if (l == 7) loc = r.w[7];
-				if (!msig) loc = 0;
-				const uint32_t l0 = __shfl_sync(0xffffffffu, loc, grp0 + 1);
-				const uint32_t l1 = __shfl_sync(0xffffffffu, loc, grp0 + 3);
-				if (live && sub == 0) st_stream_u2(a.search_out + i, make_uint2(l0, l1));
-			}
+		const unsigned lane = threadIdx.x & 31u;
+		const uint2* in = a.search_in; uint2* out = a.search_out;
+		const unsigned head = ((uintptr_t)in & 15u) ? 1u : 0u;       // tiles start at the first 16 B-aligned request
+		const bool out_vec = (((uintptr_t)out + 8u * head) & 15u) == 0;
+		const unsigned long long warp = (unsigned long long)bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
+		const unsigned long long warps = (unsigned long long)a.search_ctas * (blockDim.x >> 5);
+		uint32_t h1 = 0, h2 = 0;
+		if (head && warp == 0 && a.n_search) {
+			const uint4 v = warp_tile_load<false>(in, 1u, lane);
+			warp_tile_search<kPairs, false>(table, g, in, out, 1u, false, v, lane, h1, h2);
+		}
+		const uint2* in_a = in + head; uint2* out_a = out + head;
+		const unsigned long long n_a = a.n_search ? a.n_search - head : 0;
+		const unsigned long long tiles = (n_a + kTileReq - 1) / kTileReq;
+		unsigned long long t = warp;
+		uint4 v = make_uint4(0u, 0u, 0u, 0u);
+		if (t < tiles) v = warp_tile_load<false>(in_a + t * kTileReq, (uint32_t)min((unsigned long long)kTileReq, n_a - t * kTileReq), lane);
+		for (; t < tiles; t += warps) {
+			const uint32_t valid = (uint32_t)min((unsigned long long)kTileReq, n_a - t * kTileReq);
+			const unsigned long long tn = t + warps;
+			uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+			if (tn < tiles) vn = warp_tile_load<false>(in_a + tn * kTileReq, (uint32_t)min((unsigned long long)kTileReq, n_a - tn * kTileReq), lane);
+			warp_tile_search<kPairs, false>(table, g, in_a + t * kTileReq, out_a + t * kTileReq, valid, out_vec, v, lane, h1, h2);
+			v = vn;
+		}
+		if (st) {
+			if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
+			if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
 		}
 	} else if (bid < a.search_ctas + a.delete_ctas) {                // ---- delete, after every search
 		phase = 1;
 		cycle_wait(a.counters + 0, a.search_ctas);
 		const unsigned long long stride = (unsigned long long)a.delete_ctas * blockDim.x;
+		if (kPairs) {                                                // two lanes per request
+			const unsigned long long n_up = (a.n_delete + 15ULL) & ~15ULL;
+			for (unsigned long long i = ((unsigned long long)(bid - a.search_ctas) * blockDim.x + threadIdx.x) >> 1; i < n_up; i += stride >> 1) {
+				const bool have = i < a.n_delete;
+				uint32_t x = 0, y = 0, w = 0;
+				if (have) { x = ld_stream_u32(a.delete_in + 3 * i); y = ld_stream_u32(a.delete_in + 3 * i + 1); w = ld_stream_u32(a.delete_in + 3 * i + 2); }
+				const int z = delete_pair(table, g, have, x, y, w, threadIdx.x & 31u);
+				if (st && z && (threadIdx.x & 1u) == 0) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+			}
+		} else
 		for (unsigned long long i = (unsigned long long)(bid - a.search_ctas) * blockDim.x + threadIdx.x; i < a.n_delete; i += stride) {
 			int z = delete_one<kPairs>(table, g, ld_stream_u32(a.delete_in + 3 * i), ld_stream_u32(a.delete_in + 3 * i + 1),
 					ld_stream_u32(a.delete_in + 3 * i + 2));
@@ -1230,6 +1243,14 @@ cycle_kernel(Bucket* table, Geom g, Stats* st, CycleArgs a)
 				for (unsigned long long e = first; e < cnt; e += stride)
 					insert_one<kPairs>(table, g, ld_stream_u32(p + 3 * e), ld_stream_u32(p + 3 * e + 1), ld_stream_u32(p + 3 * e + 2), st);
 				base += cnt;
+			}
+		} else if (kPairs) {                                         // two lanes per request
+			const unsigned long long n_up = (a.n_insert + 15ULL) & ~15ULL;
+			for (unsigned long long i = ((unsigned long long)ib * blockDim.x + threadIdx.x) >> 1; i < n_up; i += stride >> 1) {
+				const bool have = i < a.n_insert;
+				uint32_t x = 0, y = 0, w = 0;
+				if (have) { x = ld_stream_u32(a.insert_in + 3 * i); y = ld_stream_u32(a.insert_in + 3 * i + 1); w = ld_stream_u32(a.insert_in + 3 * i + 2); }
+				insert_pair(table, g, have, x, y, w, st, threadIdx.x & 31u);
 			}
 		} else {
 			for (unsigned long long i = (unsigned long long)ib * blockDim.x + threadIdx.x; i < a.n_insert; i += stride)

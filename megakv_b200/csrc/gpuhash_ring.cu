@@ -217,12 +217,30 @@ ring_kernel(gh::Bucket *table, gh::Geom g, RingParams P)
 		if (n_delete) {
 			group_barrier(&ctl->arrive[0], (uint32_t)cpr * nb);
 			const uint32_t *in = (const uint32_t *)s_din;
+			if (kPairs) {                                                 /* two lanes per request: the bucket is one L2 request */
+				const uint32_t n_up = (n_delete + 15u) & ~15u;
+				for (uint32_t i = (cta * blockDim.x + threadIdx.x) >> 1; i < n_up; i += (cpr * blockDim.x) >> 1) {
+					const bool have = i < n_delete;
+					uint32_t a = 0, bb = 0, c = 0;
+					if (have) { a = gh::ld_stream_u32(in + 3 * i); bb = gh::ld_stream_u32(in + 3 * i + 1); c = gh::ld_stream_u32(in + 3 * i + 2); }
+					gh::delete_pair(table, g, have, a, bb, c, lane);
+				}
+			} else
 			for (uint32_t i = cta * blockDim.x + threadIdx.x; i < n_delete; i += cpr * blockDim.x)
 				gh::delete_one<kPairs>(table, g, gh::ld_stream_u32(in + 3 * i), gh::ld_stream_u32(in + 3 * i + 1), gh::ld_stream_u32(in + 3 * i + 2));
 		} else if (threadIdx.x == 0) atomicAdd(&ctl->arrive[0], 1u);      /* counters stay in step with nb */
 		if (n_insert) {
 			group_barrier(&ctl->arrive[1], (uint32_t)cpr * nb);
 			const uint32_t *in = (const uint32_t *)s_iin;
+			if (kPairs) {
+				const uint32_t n_up = (n_insert + 15u) & ~15u;
+				for (uint32_t i = (cta * blockDim.x + threadIdx.x) >> 1; i < n_up; i += (cpr * blockDim.x) >> 1) {
+					const bool have = i < n_insert;
+					uint32_t a = 0, bb = 0, c = 0;
+					if (have) { a = gh::ld_stream_u32(in + 3 * i); bb = gh::ld_stream_u32(in + 3 * i + 1); c = gh::ld_stream_u32(in + 3 * i + 2); }
+					gh::insert_pair(table, g, have, a, bb, c, nullptr, lane);
+				}
+			} else
 			for (uint32_t i = cta * blockDim.x + threadIdx.x; i < n_insert; i += cpr * blockDim.x)
 				gh::insert_one<kPairs>(table, g, gh::ld_stream_u32(in + 3 * i), gh::ld_stream_u32(in + 3 * i + 1), gh::ld_stream_u32(in + 3 * i + 2), nullptr);
 		} else if (threadIdx.x == 0) atomicAdd(&ctl->arrive[1], 1u);

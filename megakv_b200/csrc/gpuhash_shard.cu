@@ -319,7 +319,29 @@ serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *
 		prefix[G] = acc;
 	}
 	__syncthreads();
-	if (ok) {
+	if (ok && kPairs && kOp != 0) {
+		/* updates, pair layout: two lanes per request (gh::insert_pair / gh::delete_pair: the bucket is one L2 request);
+		 * the trip count is warp-uniform, lanes past the end idle but take part in the shuffles */
+		const uint32_t total = prefix[G], total_up = (total + 15u) & ~15u;
+		const unsigned lane = threadIdx.x & 31u;
+		int s = 0;
+		for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; e < total_up; e += (gridDim.x * blockDim.x) >> 1) {
+			const bool have = e < total;
+			uint32_t a = 0, b = 0, c = 0;
+			if (have) {
+				while (e >= prefix[s + 1]) s++;
+				const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)(e - prefix[s]);
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(p) : "memory");
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(b) : "l"(p + 1) : "memory");
+				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(p + 2) : "memory");
+			}
+			if (kOp == 1) gh::insert_pair(table, g, have, a, b, c, st, lane);
+			else {
+				const int z = gh::delete_pair(table, g, have, a, b, c, lane);
+				if (st && z && (lane & 1u) == 0) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+			}
+		}
+	} else if (ok) {
 		const uint32_t total = prefix[G];
 		int s = 0;
 		for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -935,7 +957,7 @@ extern "C" int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int
 	if (op == 0) { if (fill_ptrs(O, seg_out_ptrs, G)) return -1; }
 	else for (int k = 0; k < kMaxShards; k++) O.p[k] = nullptr;
 	gh::Geom gg; gg.hash_mask = g->hash_mask; gg.block_mask = g->block_mask; gg.algo = g->algo; gg.max_cuckoo = g->max_cuckoo; gg.layout = g->layout;
-	const unsigned blocks = grid_for(max_total ? max_total : 1, 8);
+	const unsigned blocks = grid_for((max_total ? max_total : 1) * 2, 8);      /* updates: two lanes per request (pair layout) */
 	cudaStream_t s = (cudaStream_t)stream;
 	gh::Bucket *t = (gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
 	const bool pairs = gg.layout == gh::kLayoutPairs;

@@ -423,8 +423,10 @@ extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
 	a.insert_in = (const uint32_t *)ielem_d; a.n_insert = n_insert;
 	a.blk_input = (const uint32_t *const *)blk_input_d; a.blk_elem_num = blk_elem_num_d; a.num_blks = num_blks;
 	const size_t sms = (size_t)sm_count_now();
-	size_t sc = (n_search * 4 + 255) / 256, dc = (n_delete + 255) / 256, ic = (n_insert + 255) / 256;
-	if (sc > sms * 32) sc = sms * 32;
+	const size_t upl = g->layout == GPUHASH_LAYOUT_PAIRS ? 2 : 1;               /* lanes per update request */
+	size_t sc = ((n_search + gh::kTileReq - 1) / gh::kTileReq + 7) / 8;          /* 8 warps per CTA, one 64-request tile per warp and round */
+	size_t dc = (n_delete * upl + 255) / 256, ic = (n_insert * upl + 255) / 256;
+	if (sc > sms * 8) sc = sms * 8;
 	if (dc > sms * 8) dc = sms * 8;
 	if (ic > sms * 8) ic = sms * 8;
 	if (blk_input_d) ic = sms * (size_t)(g_tune.insert_ctas_per_sm > 0 ? g_tune.insert_ctas_per_sm : 4);
