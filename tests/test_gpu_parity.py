@@ -616,3 +616,37 @@ def test_fold_keys_matches_receiver_derivation(gpu, nkey, stride, fold, rng):
     got = out_d.download(np.uint32).view(mk.SEL_DT)
     want = po.fold_keys(raw[:, :nkey], bool(fold))
     assert np.array_equal(got["sig"], want["sig"]) and np.array_equal(got["hash"], want["hash"])
+
+
+@pytest.mark.parametrize("mem_p", [26, 28], ids=["L2-resident", "beyond-L2"])
+def test_config2_zipf_mixed_two_choice(gpu, layout, mem_p, rng):
+    """BASELINE configs[2]: zipf(0.99) mixed insert/search, HASH_2CHOICE, a table that fits in L2 (64 MiB) and one that
+    does not (256 MiB).  Rounds of {search batch, then insert batch} through the scheduler-cycle call; hot keys repeat
+    many times inside one batch, so every SET of a key in a round carries the same new location (the outcome is then
+    independent of which duplicate wins) and every search word of every round must equal the oracle's."""
+    from megakv_b200 import keystream as ks
+    pop = (1 << mem_p) // 8 // 4                                   # load factor 0.25
+    o = po.Oracle(mem_p, po.TWO_CHOICE)
+    ix = mk.GpuHashIndex(mem_p, algo=po.TWO_CHOICE, workers=1, max_search=1 << 17, max_insert=1 << 17, max_delete=8, layout=layout)
+    try:
+        chunk = 1 << 20
+        for first in range(0, pop, chunk):
+            iel, _ = ks.uniform_inserts(3, first, min(chunk, pop - first))
+            o.insert_mt(iel, 8)
+        ix.load(o.table)
+        z = ks.Zipf(pop, 0.99, rng)
+        for rnd in range(1, 6):
+            sel = ks.keys_to_requests(ks._keys_at(3, z.ranks(60000)))
+            idx = z.ranks(20000)
+            fresh_idx = pop + (rnd - 1) * 3000 + np.arange(3000)   # 13 % of the SETs are new keys
+            allidx = np.concatenate([idx, fresh_idx])
+            rng.shuffle(allidx)
+            iel, _ = ks.keys_to_requests(ks._keys_at(3, allidx), (allidx + 1 + rnd * (1 << 27)).astype(np.uint64))
+            want = o.search(sel)
+            got = ix.cycle(search=sel, insert=iel)
+            o.insert(iel)
+            assert np.array_equal(got, want), f"round {rnd}"
+            assert (want.reshape(-1, 2) != 0).any(axis=1).mean() > 0.99
+        assert o.digest(table=ix.dump()) == o.digest()
+    finally:
+        ix.close()
