@@ -330,7 +330,7 @@ def main():
     roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": round(N_SEARCH * bytes_per_search),
-            "kernel": "gh::search_quad_staged_kernel<pairs>", "peak_source": peak_src, "bytes_per_search": round(bytes_per_search, 2),
+            "kernel": "gh::search_warp_kernel<pairs>", "peak_source": peak_src, "bytes_per_search": round(bytes_per_search, 2),
             "launches": steps, "avg_launch_us_effective": round(t_s / steps * 1e6, 3),
             "bulk_launch": {"requests": bulk_n, "GB/s": round(bulk_gbs, 1), "Mops/s": round(bulk_mops, 1),
                             "frac": round(bulk_gbs / peak, 4)},
