@@ -40,23 +40,21 @@ N_INSERT = BATCH - N_SEARCH  # 3277 = 5 %
 SEED = 1
 
 
-_REAL_STDOUT = None
-
-
 def quiet_stdout():
     """Libraries print to stdout (NCCL: "NCCL version ..."); the contract is ONE JSON line there.  Everything written to
-    fd 1 from now on goes to stderr; emit() writes the line to the real stdout."""
-    global _REAL_STDOUT
-    if _REAL_STDOUT is None:
+    fd 1 from now on goes to stderr; emit() writes the line to the real stdout.  (The saved descriptor lives on the sys
+    module: this file is both __main__ and, for the multi-GPU arm, the imported module `bench`.)"""
+    if getattr(sys, "_megakv_real_stdout", None) is None:
         sys.stdout.flush()
-        _REAL_STDOUT = os.dup(1)
+        sys._megakv_real_stdout = os.dup(1)
         os.dup2(2, 1)
 
 
 def emit(line):
     data = (json.dumps(line) + "\n").encode()
     sys.stdout.flush()
-    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+    fd = getattr(sys, "_megakv_real_stdout", None)
+    os.write(fd if fd is not None else 1, data)
 
 
 def peaks():
