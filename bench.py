@@ -125,7 +125,7 @@ def cpu_workload(mem_p, preload_log2, steps, threads, log, warm=0):
     t0 = time.time()
     chunk = 1 << 22
     for first in range(0, pop, chunk):
-        iel, _ = po.keys(SEED, first, chunk)
+        iel, _ = po.keys(SEED, first, min(chunk, pop - first))
         o.insert_mt(iel, 8)
     log(f"cpu: preloaded 2^{preload_log2} keys into a 2^{mem_p} B table in {time.time() - t0:.1f} s")
     rng = np.random.default_rng(7)

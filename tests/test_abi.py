@@ -147,3 +147,27 @@ def test_keystream_matches_oracle_generator():
     assert np.array_equal(sel["sig"], all_iel["sig"][idx]) and np.array_equal(sel["hash"], all_iel["hash"][idx])
     counts = np.bincount(idx, minlength=100000)
     assert counts[0] > counts[10] > counts[1000] and counts[0] > 0.05 * 50000      # skewed the right way
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver reads ONE JSON line from bench.py's stdout; library chatter (NCCL prints its version there) must not
+    join it.  The reference arm runs on the host cores, so the contract can be checked here."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--mem-p", "24"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mops/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_zetan_closed_form_matches_the_sum():
+    from megakv_b200 import keystream as ks
+    n = 3_000_000
+    exact = float(np.sum(1.0 / np.power(np.arange(1, n + 1, dtype=np.float64), 0.99)))
+    assert abs(ks.zetan(n, 0.99) - exact) / exact < 1e-10
+    assert abs(ks.zetan(1000, 0.5) - float(np.sum(1.0 / np.sqrt(np.arange(1, 1001))))) < 1e-9
