@@ -79,18 +79,18 @@ class ShardedIndex:
         self.dist.all_to_all_single(inbox, packed, rs, cs, group=self.group)
         return inbox, cs, rs, perm
 
-    def search(self, sel, out=None):
+    def search(self, sel, out=None, after_serve=None):
         if self.exchange == "p2p":
-            return self.be.p2p_search(self, sel, out)
+            return self.be.p2p_search(self, sel, out, after_serve)
         inbox, cs, rs, perm = self._route(sel, 2, True)
         res = self.be.search_local(inbox, rs)                            # [sum(rs), 2]
         back = self.be.empty(sum(cs), 2)
         self.dist.all_to_all_single(back, res, cs, rs, group=self.group)
         return self.be.gather(back, cs, perm, sel.shape[0])
 
-    def insert(self, iel):
+    def insert(self, iel, before_serve=None):
         if self.exchange == "p2p":
-            return self.be.p2p_update(self, iel, insert=True)
+            return self.be.p2p_update(self, iel, insert=True, before_serve=before_serve)
         inbox, cs, rs, _ = self._route(iel, 3, False)
         self.be.insert_local(inbox, rs)
 
@@ -281,12 +281,16 @@ class CudaShardBackend:
                                 self.pp_origin_stage if op == 0 else None, n_hint or self.G * self.cap, None, None,
                                 self.rank, self.pp_peer_resf, A + self.off_ticket + 4, ix.seq, None, self._stream()), "gpuhash_serve")
 
-    def p2p_search(self, ix, sel, out=None):
-        """scatter+publish, serve (lookup + result flags), gather -- each behind a one-CTA flag wait"""
+    def p2p_search(self, ix, sel, out=None, after_serve=None):
+        """scatter+publish, serve (lookup + result flags), gather -- each behind a flag wait.  after_serve: called once
+        this rank's serve kernel is enqueued (the update exchange of the same cycle, running on its own stream, orders
+        its serve kernel behind it: the in-stream order search -> insert of the reference, mega_scheduler.c:392-502)"""
         L, N, A = self.L, self.N, self.arena.ptr
         n = sel.shape[0]
         self._p2p_scatter(ix, sel, 2, True)
         self._p2p_serve(ix, 0, 2 * max(n, 1))           # uniform keys: about n requests arrive; the grid strides if more do
+        if after_serve:
+            after_serve()
         if out is None:
             out = self.empty(n, 2)
         self._p2p_gather(ix, n, out)
@@ -303,9 +307,12 @@ class CudaShardBackend:
                                        self.plan.log2, out.data_ptr() if n else None, n, None, 0, None, self._stream()),
                 "gpuhash_route_gather")
 
-    def p2p_update(self, ix, iel, insert):
-        """scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter."""
+    def p2p_update(self, ix, iel, insert, before_serve=None):
+        """scatter+publish, serve (insert/delete + consumption ack).  The ack is awaited by the NEXT scatter.
+        before_serve: called between the two (see p2p_search)."""
         self._p2p_scatter(ix, iel, 3, False)
+        if before_serve:
+            before_serve()
         self._p2p_serve(ix, 1 if insert else 2, 2 * max(iel.shape[0], 1))
 
     def p2p_error(self):

@@ -61,6 +61,13 @@ def main(args, rank, world, local_rank, log):
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    # GPUHASH_SPLIT_UPDATES=1 (experiment): the update exchange of a cycle runs next to its search exchange -- own (small)
+    # inboxes, flags and stream per lane; only its serve kernel waits (event) for this rank's search serve kernel of the
+    # same cycle, which keeps the reference's in-stream order search -> insert at every owner for every origin.
+    # Measured on 2 GPUs, 8 lanes: 33.0 vs 33.3 Gops/s without -- the other lanes fill those gaps already.  Off.
+    split_updates = os.environ.get('GPUHASH_SPLIT_UPDATES', '0') != '0'
+    ulanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * N_INSERT, table=be.table), plan, exchange="p2p") for _ in range(S)] if split_updates else []
+    ustreams = [torch.cuda.Stream(device=dev) for _ in range(S)] if split_updates else []
     ixc = ShardedIndex(lanes[0].be, plan, exchange="collective")  # same table and buffers, NCCL exchange (baseline)
 
     # ---- preload through the routed insert path: rank r inserts key indices r, r + world, ... in chunks
@@ -104,14 +111,23 @@ def main(args, rank, world, local_rank, log):
                     index.insert(ins_f[b * N_INSERT:(b + g) * N_INSERT])
             return
         cur = torch.cuda.current_stream()
-        for st in streams:
+        for st in streams + ustreams:
             st.wait_stream(cur)
         for c, (b, g) in enumerate(cycles_of(first, count)):
-            with torch.cuda.stream(streams[c % S]):
-                lanes[c % S].search(sel_f[b * N_SEARCH:(b + g) * N_SEARCH], out_f[b * N_SEARCH:(b + g) * N_SEARCH])
+            k = c % S
+            sq, oq, iq = sel_f[b * N_SEARCH:(b + g) * N_SEARCH], out_f[b * N_SEARCH:(b + g) * N_SEARCH], ins_f[b * N_INSERT:(b + g) * N_INSERT]
+            if with_insert and split_updates:
+                ev = torch.cuda.Event()
+                with torch.cuda.stream(streams[k]):
+                    lanes[k].search(sq, oq, after_serve=lambda: ev.record(torch.cuda.current_stream()))
+                with torch.cuda.stream(ustreams[k]):
+                    ulanes[k].insert(iq, before_serve=lambda: torch.cuda.current_stream().wait_event(ev))
+                continue
+            with torch.cuda.stream(streams[k]):
+                lanes[k].search(sq, oq)
                 if with_insert:
-                    lanes[c % S].insert(ins_f[b * N_INSERT:(b + g) * N_INSERT])
-        for st in streams:
+                    lanes[k].insert(iq)
+        for st in streams + ustreams:
             cur.wait_stream(st)
 
     def timed(index, first, count, graph, with_insert=True):
@@ -164,7 +180,7 @@ def main(args, rank, world, local_rank, log):
     with sampler:
         t_val = timed(None, warm, steps, use_graph)
     value = world * steps * BATCH / t_val / 1e6
-    err = be.p2p_error() + sum(l.be.p2p_error() for l in lanes)
+    err = be.p2p_error() + sum(l.be.p2p_error() for l in lanes + ulanes)
     assert err == 0, "a flag wait timed out"
     chk = out[(warm + steps - 1) % kd].cpu().numpy().view(np.uint32)
     hit = float(((chk[:, 0] != 0) | (chk[:, 1] != 0)).mean())
@@ -273,6 +289,7 @@ def main(args, rank, world, local_rank, log):
                            f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
                            f"per GPU and step {N_SEARCH} searches + {N_INSERT} inserts")
         cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph, "lanes": S,
+                    "update_exchange": "own stream per lane, serve ordered behind the search serve" if split_updates else "same stream as the searches",
                     "batches_per_exchange": GROUP, "wait_mode": "stream mem-ops" if L.gpuhash_wait_mode() == 1 else "kernel",
                     "parallelism": f"shard{world}"})
         line = {
