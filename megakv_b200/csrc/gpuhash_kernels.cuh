@@ -113,6 +113,15 @@ __device__ __forceinline__ void st_stream_u2(uint2* p, uint2 v)
 	asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// Programmatic dependent launch: let the next kernel of the stream be scheduled while this one runs, and do not touch
+// anything the previous kernel of the stream wrote before it has completed.  Both are no-ops in a launch without the
+// programmatic-serialization attribute (libgpuhash.cu: GPUHASH_PDL).
+__device__ __forceinline__ void pdl_enter()
+{
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 /* ------------------------------------------------------------------ geometry */
 
 // gpu_hash.cu:55
@@ -659,6 +668,7 @@ insert_segments_kernel(Bucket* table, const uint32_t* const* __restrict__ blk_in
 __global__ void __launch_bounds__(256)
 insert_flat_pair_kernel(Bucket* table, const uint32_t* __restrict__ in, size_t n, Geom g, Stats* st)
 {
+	pdl_enter();
 	const unsigned lane = threadIdx.x & 31u;
 	const size_t per_iter = ((size_t)gridDim.x * blockDim.x) >> 1;
 	const size_t n_up = (n + 15) & ~(size_t)15;
@@ -1079,6 +1089,7 @@ search_warp_kernel(const uint2* __restrict__ in, void* __restrict__ out_,
 {
 	constexpr size_t kOutBytes = kCompact ? 4 : 8;               // per request
 	char* out = (char*)out_;
+	pdl_enter();
 	const unsigned lane = threadIdx.x & 31u;
 	const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
 	uint32_t h1 = 0, h2 = 0;

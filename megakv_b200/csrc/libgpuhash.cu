@@ -83,6 +83,26 @@ static int update_pair_default(void)
 	if (v < 0) { const char *e = getenv("GPUHASH_UPDATE_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
 	return v;
 }
+/* GPUHASH_PDL=1: the search and insert launches of a stream are chained by programmatic dependent launch -- the next
+ * kernel's CTAs are scheduled while the previous kernel still runs and wait (griddepcontrol.wait) for its completion, so
+ * the launch latency between the small kernels of a 64 K batch is hidden.  Captured into CUDA graphs as programmatic edges. */
+static int pdl_on(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("GPUHASH_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+	return v;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t s, Args... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = pdl_on();
+	cfg.attrs = at; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 /* GPUHASH_SEARCH_QPT=<n>: process-wide override of tune.search_qpt == 0 (A/B runs of the launch shapes) */
 static int qpt_env(void)
 {
@@ -192,8 +212,8 @@ extern "C" int gpuhash_search_ex(const gpuhash_geom_t *g, const void *selem_d, v
 		size_t blocks = (tiles + wpc - 1) / wpc, cap = (size_t)sm_count_now() * (2048 / threads);
 		if (blocks > cap) blocks = cap;
 		if (blocks == 0) blocks = 1;
-		if (g->layout == GPUHASH_LAYOUT_PAIRS) gh::search_warp_kernel<true><<<(unsigned)blocks, threads, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
-		else                                   gh::search_warp_kernel<false><<<(unsigned)blocks, threads, 0, s>>>(in, out, t, n, gg, st, head, out_vec);
+		if (g->layout == GPUHASH_LAYOUT_PAIRS) launch_pdl(gh::search_warp_kernel<true, false>, (unsigned)blocks, threads, s, in, (void *)out, t, n, gg, st, head, out_vec);
+		else                                   launch_pdl(gh::search_warp_kernel<false, false>, (unsigned)blocks, threads, s, in, (void *)out, t, n, gg, st, head, out_vec);
 		return (int)cudaGetLastError();
 	}
 	if (qpt == -5 && ((uintptr_t)in & 7u) == 0 && ((uintptr_t)out & 7u) == 0) {
@@ -321,7 +341,7 @@ extern "C" int gpuhash_insert_flat_ex(const gpuhash_geom_t *g, void *table_d, co
 		if (gg.layout == gh::kLayoutPairs && update_pair_default()) {
 			blocks = (2 * n + 255) / 256;
 			if (blocks > cap) blocks = cap;
-			gh::insert_flat_pair_kernel<<<(unsigned)blocks, 256, 0, s>>>((gh::Bucket *)table_d, (const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
+			launch_pdl(gh::insert_flat_pair_kernel, (unsigned)blocks, 256u, s, (gh::Bucket *)table_d, (const uint32_t *)ielem_d, n, gg, (gh::Stats *)stats_d);
 			return (int)cudaGetLastError();
 		}
 		if (blocks > cap) blocks = cap;
