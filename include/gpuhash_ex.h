@@ -186,7 +186,8 @@ int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_
  * or a negative error, and blocks only while the ring is full.  Batches of one ring run strictly in order, each as
  * search -> delete -> insert (the reference's per-stream order, mega_scheduler.c:392-502); rings are unordered against
  * each other.  The kernel parks itself after idle_ms without a doorbell (default 2000) and is relaunched on demand.
- * One ring object per device at a time. */
+ * One ring object per device at a time; the calls of one ring object come from one host thread (the scheduler thread of
+ * the reference, src/mega.c:410) -- there is no locking inside. */
 typedef struct gpuhash_ring_s gpuhash_ring_t;
 gpuhash_ring_t *gpuhash_ring_create(const gpuhash_geom_t *g, void *table_d, int rings, int slots, int ctas_per_sm, unsigned idle_ms);
 long long gpuhash_ring_submit(gpuhash_ring_t *q, int ring,

@@ -650,3 +650,41 @@ def test_config2_zipf_mixed_two_choice(gpu, layout, mem_p, rng):
         assert o.digest(table=ix.dump()) == o.digest()
     finally:
         ix.close()
+
+
+@pytest.mark.parametrize("zero_copy", [0, 1])
+def test_index_compact_results_mode(gpu, layout, zero_copy, rng):
+    """gpuhash_index_set_compact_results: search_out_h gets ONE word per request (mega_send.c:411-414's choice), through
+    staging copies and through zero-copy, with deletes and inserts of the same cycle still applied in order."""
+    L = N.lib()
+    mem_p = 22
+    o = po.Oracle(mem_p)
+    ix = mk.GpuHashIndex(mem_p, workers=1, max_search=1 << 17, max_insert=1 << 16, max_delete=1 << 16, layout=layout)
+    base = H.random_requests(rng, 60000)
+    ix.insert(base); o.insert(base)
+    L.gpuhash_index_set_zero_copy(ix.h, zero_copy); L.gpuhash_index_set_compact_results(ix.h, 1)
+    n_s, n_i, n_d = 62259, 3277, 500
+    hs = L.gpuhash_host_alloc(8 * n_s); ho = L.gpuhash_host_alloc(4 * n_s + 16)
+    hi = L.gpuhash_host_alloc(12 * n_i); hd = L.gpuhash_host_alloc(12 * n_d)
+    try:
+        s_np = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_uint32)), shape=(2 * n_s,))
+        o_np = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_uint32)), shape=(n_s + 4,))
+        i_np = np.ctypeslib.as_array(C.cast(hi, C.POINTER(C.c_uint32)), shape=(3 * n_i,))
+        d_np = np.ctypeslib.as_array(C.cast(hd, C.POINTER(C.c_uint32)), shape=(3 * n_d,))
+        for rnd in range(2):
+            fresh = H.random_requests(rng, n_i, loc_base=2000000 + rnd * n_i)
+            sel = np.concatenate([H.to_sel(base), H.to_sel(H.random_requests(rng, 5000))])[rng.integers(0, 65000, n_s)]
+            dele = base[rnd * n_d:(rnd + 1) * n_d]
+            s_np[:] = sel.view(np.uint32); i_np[:] = fresh.view(np.uint32).reshape(-1); d_np[:] = dele.view(np.uint32).reshape(-1)
+            o_np[:] = 0xDEADBEEF
+            want = po.compact_results(o.search(sel)); o.delete(dele); o.insert(fresh)
+            N.check(L.gpuhash_index_submit(ix.h, 0, hs, n_s, ho, hd, n_d, hi, n_i))
+            ix.sync()
+            assert np.array_equal(o_np[:n_s], want), f"round {rnd}"
+            assert np.all(o_np[n_s:] == 0xDEADBEEF)
+        L.gpuhash_index_set_compact_results(ix.h, 0)
+        assert o.digest(table=ix.dump()) == o.digest()
+    finally:
+        for p_ in (hs, ho, hi, hd):
+            L.gpuhash_host_free(p_)
+        ix.close()
