@@ -330,10 +330,9 @@ serve_kernel(gh::Bucket *table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *
 			uint32_t a = 0, b = 0, c = 0;
 			if (have) {
 				while (e >= prefix[s + 1]) s++;
+				/* the inbox was complete before this kernel was launched (flag wait in the stream): ordinary coalescing loads */
 				const uint32_t *p = (const uint32_t *)seg_in.p[s] + 3 * (size_t)(e - prefix[s]);
-				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(p) : "memory");
-				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(b) : "l"(p + 1) : "memory");
-				asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(p + 2) : "memory");
+				a = gh::ld_stream_u32(p); b = gh::ld_stream_u32(p + 1); c = gh::ld_stream_u32(p + 2);
 			}
 			if (kOp == 1) gh::insert_pair(table, g, have, a, b, c, st, lane);
 			else {
