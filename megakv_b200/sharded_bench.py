@@ -54,10 +54,11 @@ def main(args, rank, world, local_rank, log):
     # with the batches of all its workers (mega_scheduler.c:392-502 loops over cpu_worker_num <= 16 buffers per cycle).
     # A graph node costs ~2 us of front-end time here and a routed batch needs ten of them, so per-batch exchanges are
     # node-bound (2 GPUs: 22 us per 64 K batch however many lanes); per-cycle exchanges are not.
-    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 8)), 16))
-    # 64 batches per exchange when the run is long enough to keep every lane busy for at least two exchanges
-    # (2 GPUs, 8 lanes: 16 batches 25.6, 32: 31.1, 64: 33.6 Gops/s -- every kernel and flag wait has a fixed cost)
-    GROUP = int(os.environ.get('GPUHASH_GROUP', 0)) or min(64, max(4, steps // (2 * S)))
+    # 64 batches per exchange (2 GPUs, 8 lanes: 16 batches 25.6, 32: 31.1, 64: 33.6 Gops/s -- every kernel and flag wait
+    # has a fixed cost); a short run (--steps below 128) is cut into two exchanges rather than into many small ones, and
+    # takes only as many lanes as it has exchanges
+    GROUP = int(os.environ.get('GPUHASH_GROUP', 0)) or min(64, max(1, (steps + 1) // 2))
+    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 8)), 16, -(-steps // GROUP)))
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
