@@ -7,9 +7,14 @@
  *
  * Work decomposition (DESIGN.md "Kernels"):
  *   reference: 8 lanes per request, one 4 B load per lane, ballot, __syncthreads
- *   here:      one thread per request.  A 64 B bucket is two 256-bit loads (LDG.E.256,
- *              new on sm_100) held in 16 registers and matched with 8 compares, so a
- *              warp has 32 requests x 2 buckets in flight per load group instead of 4.
+ *   here:      what the memory system counts decides the shape (profiles/r01_l2_requests.md: a random probe costs one
+ *              128 B line fill and one L2 request per load INSTRUCTION that touches the line).
+ *              search: four lanes per request, lane j loads sector j of {b1.lo, b1.hi, b2.lo, b2.hi} with one
+ *                      LDG.E.256 -- each bucket is one request; a warp owns a 64-request tile (warp_tile_search).
+ *              insert/delete (pair layout): two lanes per request, the bucket again one request, the even lane
+ *                      commits with a 64-bit CAS (insert_pair / delete_pair).
+ *              One thread per request (a bucket = two 256-bit loads in 16 registers) remains for the reference byte
+ *              layout, L2-resident tables and the serial parity kernels.
  *
  * Table layouts (Geom::layout; DESIGN.md "Table layout", profiles/r01_*):
  *   kLayoutPairs  slot l of a bucket is the 8-byte pair {sig, loc} at byte 8*l.  One 64-bit CAS
