@@ -163,6 +163,41 @@ int main(int argc, char **argv)
 			for (int k = 0; k < S; k++) { cudaStreamDestroy(st[k]); cudaEventDestroy(done[k]); }
 			cudaEventDestroy(e0); cudaEventDestroy(e1);
 		}
+		// the same bytes as ONE batch per direction and cycle (32 workers x 498 KB), each direction on its own stream:
+		// plain cudaMemcpyAsync calls back to back, and cudaMemcpyBatchAsync
+		for (int batch_api = 0; batch_api <= 1; batch_api++) {
+			cudaStream_t up, dn; cudaEvent_t e0, e1, ed;
+			CK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&dn, cudaStreamNonBlocking));
+			CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreateWithFlags(&ed, cudaEventDisableTiming));
+			const int W = 32, cycles = 8;
+			void *dsts_u[W], *srcs_u[W], *dsts_d[W], *srcs_d[W]; size_t sizes[W];
+			for (int w = 0; w < W; w++) {
+				dsts_u[w] = (char *)d0 + (size_t)w * step; srcs_u[w] = (char *)h0 + (size_t)w * step;
+				dsts_d[w] = (char *)h1 + (size_t)w * step; srcs_d[w] = (char *)d1 + (size_t)w * step; sizes[w] = step;
+			}
+			float ms = 0; bool ok = true;
+			for (int pass = 0; pass < 2 && ok; pass++) {
+				CK(cudaDeviceSynchronize());
+				CK(cudaEventRecord(e0, up)); CK(cudaStreamWaitEvent(dn, e0, 0));
+				for (int c = 0; c < cycles && ok; c++) {
+					if (batch_api) {
+						cudaMemcpyAttributes at; memset(&at, 0, sizeof at); at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+						size_t idx0 = 0, fail = 0;
+						cudaError_t e = cudaMemcpyBatchAsync(dsts_u, srcs_u, sizes, W, &at, &idx0, 1, &fail, up);
+						if (e == cudaSuccess) e = cudaMemcpyBatchAsync(dsts_d, srcs_d, sizes, W, &at, &idx0, 1, &fail, dn);
+						if (e != cudaSuccess) { printf("      cudaMemcpyBatchAsync: %s\n", cudaGetErrorString(e)); cudaGetLastError(); ok = false; }
+					} else {
+						for (int w = 0; w < W; w++) CK(cudaMemcpyAsync(dsts_u[w], srcs_u[w], step, cudaMemcpyHostToDevice, up));
+						for (int w = 0; w < W; w++) CK(cudaMemcpyAsync(dsts_d[w], srcs_d[w], step, cudaMemcpyDeviceToHost, dn));
+					}
+				}
+				CK(cudaEventRecord(ed, dn)); CK(cudaStreamWaitEvent(up, ed, 0)); CK(cudaEventRecord(e1, up)); CK(cudaEventSynchronize(e1));
+				CK(cudaEventElapsedTime(&ms, e0, e1));
+			}
+			if (ok) printf("      32 x 498 KB per direction and cycle, one stream per direction, %s: %.1f GB/s per direction\n",
+					batch_api ? "cudaMemcpyBatchAsync" : "cudaMemcpyAsync calls", cycles * W * (double)step / 1e9 / (ms / 1e3));
+			cudaStreamDestroy(up); cudaStreamDestroy(dn); cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ed);
+		}
 		// zero-copy kernels on this memory
 		void *hd0, *hd1; CK(cudaHostGetDevicePointer(&hd0, h0, 0)); CK(cudaHostGetDevicePointer(&hd1, h1, 0));
 		for (int mode = 1; mode <= 3; mode++) {
