@@ -27,6 +27,11 @@ $(LIBDIR)/libgpuhash.so: $(OBJS)
 $(LIBDIR)/libgpuhash.a: $(OBJS)
 	ar rcs $@ $(OBJS)
 
+# a plain-C host that drives the library like Mega-KV's scheduler (legacy ABI, index_submit, ring); static archive + cudart
+example: $(LIBDIR)/libgpuhash.a
+	gcc -O2 -std=gnu99 -Wall -Iinclude -I/usr/local/cuda/include examples/scheduler_cycle.c $(LIBDIR)/libgpuhash.a \
+	    -L/usr/local/cuda/lib64 -lcudart -lrt -lpthread -ldl -o examples/scheduler_cycle
+
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
@@ -36,4 +41,4 @@ ref:
 clean:
 	rm -rf $(LIBDIR) ; $(MAKE) -C oracle clean
 
-.PHONY: all oracle ref clean
+.PHONY: all example oracle ref clean

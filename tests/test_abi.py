@@ -171,3 +171,18 @@ def test_zetan_closed_form_matches_the_sum():
     exact = float(np.sum(1.0 / np.power(np.arange(1, n + 1, dtype=np.float64), 0.99)))
     assert abs(ks.zetan(n, 0.99) - exact) / exact < 1e-10
     assert abs(ks.zetan(1000, 0.5) - float(np.sum(1.0 / np.sqrt(np.arange(1, 1001))))) < 1e-9
+
+
+def test_c_host_example_compiles_and_links_statically(native, tmp_path):
+    """examples/scheduler_cycle.c -- a C99 host using the legacy ABI, gpuhash_index_submit and gpuhash_ring_submit the way
+    Mega-KV's scheduler would -- builds with plain gcc against the static archive and cudart only (the reference's link
+    line, src/Makefile:26,67-75: no libstdc++)."""
+    if not os.path.exists(os.path.join(CUDA_LIB, "libcudart.so")):
+        pytest.skip("CUDA runtime not present")
+    exe = tmp_path / "scheduler_cycle"
+    subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-Wall", "-Werror", "-I", INC, "-I", CUDA_INC,
+                           os.path.join(ROOT, "examples", "scheduler_cycle.c"),
+                           os.path.join(ROOT, "megakv_b200", "lib", "libgpuhash.a"),
+                           "-L", CUDA_LIB, "-lcudart", "-lrt", "-lpthread", "-ldl", "-o", str(exe)])
+    needed = subprocess.check_output(["ldd", str(exe)], text=True)
+    assert "libstdc++" not in needed and "libgpuhash" not in needed

@@ -688,3 +688,21 @@ def test_index_compact_results_mode(gpu, layout, zero_copy, rng):
         for p_ in (hs, ho, hi, hd):
             L.gpuhash_host_free(p_)
         ix.close()
+
+
+@pytest.mark.parametrize("mode", ["legacy", "submit", "ring"])
+def test_c_host_example_runs_all_three_integration_levels(gpu, mode, tmp_path):
+    """examples/scheduler_cycle.c on the GPU: the reference's own launch loop against the legacy ABI, the one-call-per-
+    worker cycle, and the launch-free ring; every GET must come back with the location that was SET (the property
+    libgpuhash/test/insert_test.c:178-195 checks).  The program exits non-zero on any wrong result."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "scheduler_cycle"
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(root, "examples", "scheduler_cycle.c"), os.path.join(root, "megakv_b200", "lib", "libgpuhash.a"),
+                           "-L", cuda_lib, "-lcudart", "-lrt", "-lpthread", "-ldl", "-o", str(exe)])
+    env = dict(os.environ); env["LD_LIBRARY_PATH"] = cuda_lib + ":" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([str(exe), mode, "4", "8", "26"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 wrong results" in r.stdout
