@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ops", action="store_true", help="skip the per-operation bulk launches")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own search kernel (oracle/_ref)")
     ap.add_argument("--no-ring", action="store_true", help="skip the persistent-kernel ring variant of the e2e leg")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -335,6 +336,45 @@ def main():
             "random_sector_probe": {"Gsectors/s": round(sector_rate / 1e9, 2), "GB/s": round(sector_rate * 32 / 1e9, 1),
                                     "search_frac_of_probe": round(steps * N_SEARCH * (2 + hits_per_search) / t_s / sector_rate, 4),
                                     "bulk_frac_of_probe": round(bulk_n * (2 + hits_per_search) / (res.total_ms / 1e3) / sector_rate, 4)}}
+
+    # ---- the reference's OWN search kernel on the same GPU, same table, same batches (SURVEY 8d iii): gpu_hash.cu compiled
+    #      where it lies in legacy-warp mode (oracle/Makefile -> oracle/_ref/, the only way its __ballot assembles), driven
+    #      with the reference's launch shape (24576 threads, 256 per block, mega.c:163-165) and the caller's memset
+    #      (mega_scheduler.c:406).  A reported baseline and a full-size parity check (its result words == ours), nothing more;
+    #      its batch insert kernel hangs on sm_100, so only search is timed.
+    ref_gpu = None
+    ref_so = os.path.join(ROOT, "oracle", "_ref", f"libgpuhash_ref_cuckoo_{mem_p}.so")
+    if os.path.exists(ref_so) and not args.no_ref_gpu and not args.no_cpu:    # part of the baseline leg: the only one that may run oracle/
+        try:
+            R = C.CDLL(ref_so)
+            R.gpu_hash_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            R.gpu_hash_search.restype = None
+            ours = np.empty(2 * N_SEARCH, dtype=np.uint32)
+            N.check(L.gpuhash_search_ex(C.byref(geom), search_d.ptr, out_d.ptr, table, N_SEARCH, None, None)); N.check(L.gpuhash_device_sync())
+            N.check(L.gpuhash_d2h(ours.ctypes.data, out_d.ptr, ours.nbytes, None)); N.check(L.gpuhash_device_sync())
+            N.check(L.gpuhash_table_convert(C.byref(geom), table, N.LAYOUT_REFERENCE, None)); N.check(L.gpuhash_device_sync())
+            try:
+                nb = min(kd, 200)
+
+                def ref_batches():
+                    for b in range(nb):
+                        N.check(L.gpuhash_dev_memset(out_d.ptr + 8 * N_SEARCH * b, 0, 8 * N_SEARCH, None))
+                        R.gpu_hash_search(search_d.ptr + 8 * N_SEARCH * b, out_d.ptr + 8 * N_SEARCH * b, table, N_SEARCH, 24576, 256, None)
+                ref_batches(); N.check(L.gpuhash_device_sync())
+                t0 = time.perf_counter(); ref_batches(); N.check(L.gpuhash_device_sync()); t_ref = time.perf_counter() - t0
+                theirs = np.empty(2 * N_SEARCH, dtype=np.uint32)
+                N.check(L.gpuhash_d2h(theirs.ctypes.data, out_d.ptr, theirs.nbytes, None)); N.check(L.gpuhash_device_sync())
+                ref_gpu = {"what": "pzrq/megakv hash_search (gpu_hash.cu:28-75) as compiled by oracle/Makefile (compute_60 PTX -> sm_100), launch shape "
+                                   "24576 x 256 + memset per batch, one stream, device-resident batches, host wall clock over "
+                                   f"{nb} batches",
+                           "Mops/s": round(nb * N_SEARCH / t_ref / 1e6, 1), "us_per_batch": round(t_ref / nb * 1e6, 2),
+                           "results_equal_ours": bool(np.array_equal(ours, theirs))}
+                log(f"reference GPU search kernel: {ref_gpu['Mops/s']} Mops/s, results equal ours: {ref_gpu['results_equal_ours']}")
+            finally:
+                as_ref = N.Geom.from_buffer_copy(bytes(geom)); as_ref.layout = N.LAYOUT_REFERENCE
+                N.check(L.gpuhash_table_convert(C.byref(as_ref), table, geom.layout, None)); N.check(L.gpuhash_device_sync())
+        except Exception as e:                                       # a baseline must never take the product line down
+            ref_gpu = {"failed": str(e)}
 
     # ---- every operation on its own, uniform and zipf(0.99) keys, one bulk launch each (north star: search, insert and
     #      delete Mops/s, absolute and against the random-access roofline).  Algorithmic sectors per op: 3.
@@ -487,6 +527,8 @@ def main():
         except Exception as e:                                        # never let the checker's environment kill the GPU line
             cpu = {"value": None, "unit": "Mops/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
 
+    if cpu is not None and ref_gpu is not None:
+        cpu["reference_gpu_search_kernel"] = ref_gpu                 # same baseline leg: the reference's kernel on this GPU
     line = {
         "metric": "batched search/insert Mops/s (95/5 GET/SET, uniform keys)",
         "value": round(value, 1), "unit": "Mops/s", "n_gpus": 1, "steps": steps, "warmup": warm,
