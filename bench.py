@@ -362,14 +362,28 @@ def main():
                         R.gpu_hash_search(search_d.ptr + 8 * N_SEARCH * b, out_d.ptr + 8 * N_SEARCH * b, table, N_SEARCH, 24576, 256, None)
                 ref_batches(); N.check(L.gpuhash_device_sync())
                 t0 = time.perf_counter(); ref_batches(); N.check(L.gpuhash_device_sync()); t_ref = time.perf_counter() - t0
+                # and the way the reference's scheduler issues them: one stream per worker, 16 at most (mega_scheduler.c:276-280)
+                st16 = [L.gpuhash_stream_create() for _ in range(16)]
+
+                def ref_batches_16():
+                    for b in range(nb):
+                        s_ = st16[b % 16]
+                        N.check(L.gpuhash_dev_memset(out_d.ptr + 8 * N_SEARCH * b, 0, 8 * N_SEARCH, s_))
+                        R.gpu_hash_search(search_d.ptr + 8 * N_SEARCH * b, out_d.ptr + 8 * N_SEARCH * b, table, N_SEARCH, 24576, 256, s_)
+                ref_batches_16(); N.check(L.gpuhash_device_sync())
+                t0 = time.perf_counter(); ref_batches_16(); N.check(L.gpuhash_device_sync()); t_ref16 = time.perf_counter() - t0
+                for s_ in st16:
+                    L.gpuhash_stream_destroy(s_)
                 theirs = np.empty(2 * N_SEARCH, dtype=np.uint32)
                 N.check(L.gpuhash_d2h(theirs.ctypes.data, out_d.ptr, theirs.nbytes, None)); N.check(L.gpuhash_device_sync())
                 ref_gpu = {"what": "pzrq/megakv hash_search (gpu_hash.cu:28-75) as compiled by oracle/Makefile (compute_60 PTX -> sm_100), launch shape "
                                    "24576 x 256 + memset per batch, one stream, device-resident batches, host wall clock over "
                                    f"{nb} batches",
                            "Mops/s": round(nb * N_SEARCH / t_ref / 1e6, 1), "us_per_batch": round(t_ref / nb * 1e6, 2),
+                           "Mops/s_16_streams": round(nb * N_SEARCH / t_ref16 / 1e6, 1),
                            "results_equal_ours": bool(np.array_equal(ours, theirs))}
-                log(f"reference GPU search kernel: {ref_gpu['Mops/s']} Mops/s, results equal ours: {ref_gpu['results_equal_ours']}")
+                log(f"reference GPU search kernel: {ref_gpu['Mops/s']} Mops/s on one stream, {ref_gpu['Mops/s_16_streams']} on 16; "
+                    f"results equal ours: {ref_gpu['results_equal_ours']}")
             finally:
                 as_ref = N.Geom.from_buffer_copy(bytes(geom)); as_ref.layout = N.LAYOUT_REFERENCE
                 N.check(L.gpuhash_table_convert(C.byref(as_ref), table, geom.layout, None)); N.check(L.gpuhash_device_sync())
