@@ -23,7 +23,7 @@
 
 #include "gpuhash_ex.h"
 
-#define MAX_WORKERS 64
+#define MAX_WORKERS 128
 
 struct gpuhash_index_s {
 	gpuhash_geom_t geom;
