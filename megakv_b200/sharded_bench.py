@@ -289,6 +289,7 @@ def main(args, rank, world, local_rank, log):
         cfg["workload"] = (f"configs[4]: {world}xB200 sharded index, logical table 2^{plan.mem_p_total} bytes "
                            f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
                            f"per GPU and step {N_SEARCH} searches + {N_INSERT} inserts")
+        cfg["streams"] = S                                              # one stream per lane (exchange in flight)
         cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph, "lanes": S,
                     "update_exchange": "own stream per lane, serve ordered behind the search serve" if split_updates else "same stream as the searches",
                     "batches_per_exchange": GROUP, "wait_mode": "stream mem-ops" if L.gpuhash_wait_mode() == 1 else "kernel",
