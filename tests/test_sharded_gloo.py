@@ -91,7 +91,7 @@ def _worker(rank, world, port, mem_p, algo, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("algo", [po.CUCKOO, po.TWO_CHOICE])
 def test_sharded_index_matches_single_table_oracle(world, algo):
     ctx = mp.get_context("spawn")
