@@ -105,15 +105,49 @@ int gpuhash_delete_ex(const gpuhash_geom_t *g, const void *delem_d, void *table_
  * CUDA graph; gpuhash_index_create and the bench loops call it).  Idempotent, current device. */
 int gpuhash_init_device(void);
 
-/* One launch for a whole scheduler cycle of one worker (mega_scheduler.c:392-502): all searches, then all deletes,
- * then all inserts, ordered inside the kernel.  Inserts are either a flat batch (ielem_d, n_insert) or segments with
- * device-side counts (blk_input_d, blk_elem_num_d, num_blks; then ielem_d = NULL, n_insert = 0).  Any part may be empty. */
+/* ---- one launch per scheduler cycle ----
+ * The reference's cycle walks every worker's batch -- copies, gpu_hash_search, then gpu_hash_delete and gpu_hash_insert
+ * on the worker's stream -- and synchronises once (src/mega_scheduler.c:393-420, 440-502, 504).  gpuhash_cycle_multi_ex is
+ * that whole cycle as ONE kernel over a table of batch descriptors: per batch search -> delete -> insert (the reference's
+ * in-stream order), batches unordered against each other (its streams).  Tiles of 64 requests are handed to warps by an
+ * atomic ticket in phase-major order, so the kernel makes no assumption about CTA dispatch order or residency.
+ *   batches_d     the descriptor table where the DEVICE reads it (device memory: every CTA reads it)
+ *   batches_h     the same table on the host, only used to size the grid (NULL: full persistent grid)
+ *   workspace_d   gpuhash_cycle_workspace_bytes(num_batches) bytes, zeroed once by the caller; a launch leaves them zero,
+ *                 so one workspace serves one launch at a time (launches of one stream, or replays of one graph).
+ *                 Word 2 is a sticky error flag: a phase wait that exceeded GPUHASH_CYCLE_TIMEOUT_MS (default 10 s).
+ *   compact       != 0: one result word per search (the sender's choice, src/mega_send.c:411-414) instead of two
+ * Pointers inside the descriptors are device-visible: device memory or pinned host memory (zero-copy). */
+typedef struct gpuhash_batch_s {
+	const void *search_in;  void *search_out;      /* selem_t[n_search]; loc_t[2 * n_search] (compact: loc_t[n_search]) */
+	const void *delete_in;  const void *insert_in; /* delem_t[n_delete]; ielem_t[n_insert] */
+	uint32_t n_search, n_delete, n_insert, reserved;
+} gpuhash_batch_t;
+#define GPUHASH_MAX_BATCHES 128
+size_t gpuhash_cycle_workspace_bytes(int max_batches);
+/* 1 if a phase wait of a cycle kernel on the current device timed out since the last reset (read after synchronising) */
+int gpuhash_cycle_error(int reset);
+int gpuhash_cycle_multi_ex(const gpuhash_geom_t *g, void *table_d, const gpuhash_batch_t *batches_h,
+		const gpuhash_batch_t *batches_d, int num_batches, int compact, void *workspace_d,
+		gpuhash_stats_t *stats_d, void *stream);
+
+/* The cycle of ONE worker in one launch (also what the legacy gpu_delete_insert, libgpuhash.h:53-62, runs).  Inserts are
+ * either a flat batch (ielem_d, n_insert) or segments with device-side counts (blk_input_d, blk_elem_num_d, num_blks; then
+ * ielem_d = NULL, n_insert = 0).  Any part may be empty.  gpuhash_cycle_ex takes its workspace from a per-device pool
+ * (4096 slots handed out round-robin by an atomic counter): fine for direct calls; launches that are captured into CUDA
+ * graphs and replayed next to other launches should own theirs (gpuhash_cycle_ws_ex, workspace_d as above, 1 batch). */
 int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
 		const void *selem_d, size_t n_search, void *out_d,
 		const void *delem_d, size_t n_delete,
 		const void *ielem_d, size_t n_insert,
 		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
 		gpuhash_stats_t *stats_d, void *stream);
+int gpuhash_cycle_ws_ex(const gpuhash_geom_t *g, void *table_d,
+		const void *selem_d, size_t n_search, void *out_d,
+		const void *delem_d, size_t n_delete,
+		const void *ielem_d, size_t n_insert,
+		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
+		int compact, void *workspace_d, gpuhash_stats_t *stats_d, void *stream);
 
 /* ---- device / pinned memory and stream plumbing ---- */
 int   gpuhash_device_count(void);
@@ -177,6 +211,18 @@ int gpuhash_index_submit(gpuhash_index_t *ix, int worker,
 		const void *delete_in_h, size_t n_delete,
 		const void *insert_in_h, size_t n_insert);
 int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_scheduler.c:504 */
+
+/* One scheduler cycle for ALL workers in one call and ONE kernel launch (gpuhash_cycle_multi_ex): batches_h[w] holds
+ * worker w's HOST buffers and counts, as gpuhash_index_submit takes them one worker at a time.  Zero-copy mode: the
+ * buffers are pinned and the kernel reads/writes them itself; else they are staged through the index's per-worker device
+ * buffers (n_* within the capacities given to gpuhash_index_create).  Asynchronous: returns a ticket >= 0 (or a negative
+ * error); gpuhash_index_wait(ticket) returns once that cycle's results are in the host buffers -- up to
+ * GPUHASH_INDEX_SLOTS cycles may be in flight, the way the reference's triple-buffered batches allow
+ * (src/include/mega_batch.h:74-82); gpuhash_index_sync waits for everything.  Both return 0, a CUDA error, or -3 when a
+ * phase wait inside a cycle kernel timed out (the batch is suspect). */
+#define GPUHASH_INDEX_SLOTS 4
+int gpuhash_index_submit_all(gpuhash_index_t *ix, const gpuhash_batch_t *batches_h, int num_batches);
+int gpuhash_index_wait(gpuhash_index_t *ix, int ticket);
 
 /* ---- the scheduler cycle without launches (megakv_b200/csrc/gpuhash_ring.cu; north_star (c)) ----
  * `rings` descriptor rings of `slots` entries in pinned host memory feed ONE persistent kernel (ctas_per_sm CTAs per SM,
@@ -300,6 +346,20 @@ int gpuhash_bench_e2e(gpuhash_index_t *ix,
 		const void *search_h, size_t n_search, void *out_h,
 		const void *insert_h, size_t n_insert,
 		int steps, int use_graph, gpuhash_bench_result_t *res);
+
+/* Whole scheduler cycles, ONE launch per step (gpuhash_cycle_multi_ex) over `batches` worker batches: resident in device
+ * memory and timed by CUDA events (bench_cycles; steps round-robin over 1..4 streams), or end to end from pinned host
+ * memory through gpuhash_index_submit_all / gpuhash_index_wait with at most `depth` cycles in flight, timed by the HOST'S
+ * WALL CLOCK from the first submit to the return of the last wait (bench_e2e_cycles).  Batch b of step i is batch
+ * i * batches + b of the arrays (e2e: modulo host_batches). */
+int gpuhash_bench_cycles(const gpuhash_geom_t *g, void *table_d,
+		const void *search_d, size_t n_search, void *out_d,
+		const void *insert_d, size_t n_insert,
+		int batches, int steps, int streams, gpuhash_bench_result_t *res);
+int gpuhash_bench_e2e_cycles(gpuhash_index_t *ix,
+		const void *search_h, size_t n_search, void *out_h,
+		const void *insert_h, size_t n_insert,
+		int batches, size_t host_batches, int steps, int depth, gpuhash_bench_result_t *res);
 
 /* The same cycles through gpuhash_ring_submit (no launches: total_ms is host wall clock, first doorbell -> last
  * completion mark); rtt_us (optional) = median round trip of rtt_reps isolated search batches. */

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpuhash.so")
+# GPUHASH_LIB: another build of the SAME library (A/B runs of compile-time switches); never a different implementation
+LIB_PATH = os.environ.get("GPUHASH_LIB") or os.path.join(_HERE, "lib", "libgpuhash.so")
 
 CUCKOO, TWO_CHOICE = 0, 1
 LAYOUT_PAIRS, LAYOUT_REFERENCE = 0, 1
@@ -40,6 +41,11 @@ class Tune(C.Structure):                      # gpuhash_tune_t
         super().__init__(search_qpt, search_split_mode, insert_ctas_per_sm, fused_cycle)
 
 
+class Batch(C.Structure):                     # gpuhash_batch_t
+    _fields_ = [("search_in", C.c_void_p), ("search_out", C.c_void_p), ("delete_in", C.c_void_p), ("insert_in", C.c_void_p),
+                ("n_search", C.c_uint32), ("n_delete", C.c_uint32), ("n_insert", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class BenchResult(C.Structure):               # gpuhash_bench_result_t
     _fields_ = [("total_ms", C.c_float), ("search_ms", C.c_float), ("launches", C.c_ulonglong),
                 ("search_ops", C.c_ulonglong), ("insert_ops", C.c_ulonglong), ("delete_ops", C.c_ulonglong),
@@ -70,6 +76,10 @@ SYMBOLS = {
     "gpuhash_delete_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _u, _vp]),
     "gpuhash_init_device": (_i, []),
     "gpuhash_cycle_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _vp, _vp]),
+    "gpuhash_cycle_ws_ex": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "gpuhash_cycle_multi_ex": (_i, [_gp, _vp, C.POINTER(Batch), _vp, _i, _i, _vp, _vp, _vp]),
+    "gpuhash_cycle_workspace_bytes": (_sz, [_i]),
+    "gpuhash_cycle_error": (_i, [_i]),
     "gpuhash_device_count": (_i, []),
     "gpuhash_set_device": (_i, [_i]),
     "gpuhash_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
@@ -108,6 +118,8 @@ SYMBOLS = {
     "gpuhash_index_set_compact_results": (_i, [_vp, _i]),
     "gpuhash_index_submit": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gpuhash_index_sync": (_i, [_vp]),
+    "gpuhash_index_submit_all": (_i, [_vp, C.POINTER(Batch), _i]),
+    "gpuhash_index_wait": (_i, [_vp, _i]),
     "gpuhash_route_scatter": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _vp]),
     "gpuhash_route_publish": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp]),
     "gpuhash_search_segments": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),
@@ -140,6 +152,8 @@ SYMBOLS = {
     "gpuhash_gen_requests": (_i, [_vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
     "gpuhash_bench_resident": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),
     "gpuhash_bench_e2e": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, C.POINTER(BenchResult)]),
+    "gpuhash_bench_cycles": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),
+    "gpuhash_bench_e2e_cycles": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _sz, _i, _i, C.POINTER(BenchResult)]),
 }
 
 _lib = None

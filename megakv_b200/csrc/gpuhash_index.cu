@@ -25,6 +25,15 @@
 
 #define MAX_WORKERS 128
 
+struct cycle_slot {                 /* one whole-cycle launch in flight (gpuhash_index_submit_all) */
+	cudaStream_t stream;
+	cudaEvent_t done;
+	gpuhash_batch_t *desc_h;        /* pinned mirror of the descriptor table the kernel reads */
+	gpuhash_batch_t *desc_d;
+	void *ws_d;                     /* gpuhash_cycle_workspace_bytes(MAX_WORKERS), zero between launches */
+	int busy;
+};
+
 struct gpuhash_index_s {
 	gpuhash_geom_t geom;
 	void *table;
@@ -35,6 +44,9 @@ struct gpuhash_index_s {
 	void *search_out_d[MAX_WORKERS];
 	void *delete_in_d[MAX_WORKERS];
 	void *insert_in_d[MAX_WORKERS];
+	void *ws_d[MAX_WORKERS];        /* one-launch cycle of worker w: its own workspace (launches of a stream are serial) */
+	struct cycle_slot slot[GPUHASH_INDEX_SLOTS];
+	unsigned next_slot;
 	gpuhash_stats_t *stats_d;
 	int stats_on;
 	int zero_copy;       /* kernels read requests from / write results to the caller's pinned host buffers directly */
@@ -48,7 +60,14 @@ extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
 	for (int w = 0; w < ix->workers; w++) {
 		if (ix->stream[w]) cudaStreamDestroy(ix->stream[w]);
 		cudaFree(ix->search_in_d[w]); cudaFree(ix->search_out_d[w]);
-		cudaFree(ix->delete_in_d[w]); cudaFree(ix->insert_in_d[w]);
+		cudaFree(ix->delete_in_d[w]); cudaFree(ix->insert_in_d[w]); cudaFree(ix->ws_d[w]);
+	}
+	for (int k = 0; k < GPUHASH_INDEX_SLOTS; k++) {
+		struct cycle_slot *c = &ix->slot[k];
+		if (c->stream) cudaStreamDestroy(c->stream);
+		if (c->done) cudaEventDestroy(c->done);
+		if (c->desc_h) cudaFreeHost(c->desc_h);
+		cudaFree(c->desc_d); cudaFree(c->ws_d);
 	}
 	cudaFree(ix->stats_d);
 	cudaFree(ix->table);
@@ -80,13 +99,28 @@ extern "C" gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo
 	      && cudaMemset(ix->table, 0, bytes) == cudaSuccess            /* all-zero == empty, mega_scheduler.c:273-274 */
 	      && cudaMalloc((void **)&ix->stats_d, sizeof(gpuhash_stats_t)) == cudaSuccess
 	      && cudaMemset(ix->stats_d, 0, sizeof(gpuhash_stats_t)) == cudaSuccess;
+	const size_t ws1 = gpuhash_cycle_workspace_bytes(1), wsn = gpuhash_cycle_workspace_bytes(MAX_WORKERS);
 	for (int w = 0; ok && w < workers; w++) {
 		ok = cudaStreamCreateWithFlags(&ix->stream[w], cudaStreamNonBlocking) == cudaSuccess
 		  && cudaMalloc(&ix->search_in_d[w], (max_search ? max_search : 1) * 8) == cudaSuccess
 		  && cudaMalloc(&ix->search_out_d[w], (max_search ? max_search : 1) * 8) == cudaSuccess
 		  && cudaMalloc(&ix->delete_in_d[w], (max_delete ? max_delete : 1) * 12) == cudaSuccess
-		  && cudaMalloc(&ix->insert_in_d[w], (max_insert ? max_insert : 1) * 12) == cudaSuccess;
+		  && cudaMalloc(&ix->insert_in_d[w], (max_insert ? max_insert : 1) * 12) == cudaSuccess
+		  && cudaMalloc(&ix->ws_d[w], ws1) == cudaSuccess
+		  && cudaMemset(ix->ws_d[w], 0, ws1) == cudaSuccess;
 	}
+	for (int k = 0; ok && k < GPUHASH_INDEX_SLOTS; k++) {
+		struct cycle_slot *c = &ix->slot[k];
+		ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
+		  && cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) == cudaSuccess
+		  && cudaHostAlloc((void **)&c->desc_h, sizeof(gpuhash_batch_t) * MAX_WORKERS, cudaHostAllocDefault) == cudaSuccess
+		  && cudaMalloc((void **)&c->desc_d, sizeof(gpuhash_batch_t) * MAX_WORKERS) == cudaSuccess
+		  && cudaMalloc(&c->ws_d, wsn) == cudaSuccess
+		  && cudaMemset(c->ws_d, 0, wsn) == cudaSuccess;
+	}
+	/* the fills above are asynchronous to the host and every stream of the index is non-blocking (no implicit order
+	 * against the legacy stream they ran on): nothing may be submitted before they have finished */
+	if (ok) ok = cudaDeviceSynchronize() == cudaSuccess;
 	if (!ok) {
 		fprintf(stderr, "gpuhash_index_create: %s\n", cudaGetErrorString(cudaGetLastError()));
 		gpuhash_index_destroy(ix);
@@ -103,7 +137,8 @@ extern "C" int gpuhash_index_clear(gpuhash_index_t *ix)
 {
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) return (int)e;
-	return (int)cudaMemset(ix->table, 0, gpuhash_table_bytes(&ix->geom));
+	if ((e = cudaMemset(ix->table, 0, gpuhash_table_bytes(&ix->geom))) != cudaSuccess) return (int)e;
+	return (int)cudaDeviceSynchronize();          /* the fill is asynchronous to the host; the index's streams are non-blocking */
 }
 
 /* Host images are always in the reference's byte layout (bucket_t[], gpu_hash.h:79-82); the device table
@@ -153,7 +188,7 @@ extern "C" int gpuhash_index_stats(gpuhash_index_t *ix, gpuhash_stats_t *out, in
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) return (int)e;
 	if (out && (e = cudaMemcpy(out, ix->stats_d, sizeof *out, cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)e;
-	if (reset) e = cudaMemset(ix->stats_d, 0, sizeof(gpuhash_stats_t));
+	if (reset && (e = cudaMemset(ix->stats_d, 0, sizeof(gpuhash_stats_t))) == cudaSuccess) e = cudaDeviceSynchronize();
 	return (int)e;
 }
 
@@ -193,8 +228,8 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 	}
 	if (ix->zero_copy) {
 		if (tune.fused_cycle)
-			return gpuhash_cycle_ex(&ix->geom, ix->table, search_in_h, n_search, search_out_h, delete_in_h, n_delete,
-					insert_in_h, n_insert, NULL, NULL, 0, st, s);
+			return gpuhash_cycle_ws_ex(&ix->geom, ix->table, search_in_h, n_search, search_out_h, delete_in_h, n_delete,
+					insert_in_h, n_insert, NULL, NULL, 0, 0, ix->ws_d[w], st, s);
 		if (n_search && (rc = gpuhash_search_ex(&ix->geom, search_in_h, search_out_h, ix->table, n_search, st, s)) != 0) return rc;
 		if (n_delete && (rc = gpuhash_delete_ex(&ix->geom, delete_in_h, ix->table, n_delete, st, 0, s)) != 0) return rc;
 		if (n_insert && (rc = gpuhash_insert_flat_ex(&ix->geom, ix->table, insert_in_h, n_insert, st, 0, s)) != 0) return rc;
@@ -204,8 +239,8 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 		if (n_search && (e = cudaMemcpyAsync(ix->search_in_d[w], search_in_h, n_search * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
 		if (n_delete && (e = cudaMemcpyAsync(ix->delete_in_d[w], delete_in_h, n_delete * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
 		if (n_insert && (e = cudaMemcpyAsync(ix->insert_in_d[w], insert_in_h, n_insert * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
-		if ((rc = gpuhash_cycle_ex(&ix->geom, ix->table, ix->search_in_d[w], n_search, ix->search_out_d[w], ix->delete_in_d[w], n_delete,
-				ix->insert_in_d[w], n_insert, NULL, NULL, 0, st, s)) != 0) return rc;
+		if ((rc = gpuhash_cycle_ws_ex(&ix->geom, ix->table, ix->search_in_d[w], n_search, ix->search_out_d[w], ix->delete_in_d[w], n_delete,
+				ix->insert_in_d[w], n_insert, NULL, NULL, 0, 0, ix->ws_d[w], st, s)) != 0) return rc;
 		if (n_search && (e = cudaMemcpyAsync(search_out_h, ix->search_out_d[w], n_search * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
 		return 0;
 	}
@@ -225,10 +260,77 @@ extern "C" int gpuhash_index_submit(gpuhash_index_t *ix, int w,
 	return 0;
 }
 
-extern "C" int gpuhash_index_sync(gpuhash_index_t *ix)
+static int cycle_error(gpuhash_index_t *ix)
 {
 	(void)ix;
-	return (int)cudaDeviceSynchronize();                                       /* mega_scheduler.c:504 */
+	return gpuhash_cycle_error(1) ? -3 : 0;
+}
+
+extern "C" int gpuhash_index_sync(gpuhash_index_t *ix)
+{
+	cudaError_t e = cudaDeviceSynchronize();                                   /* mega_scheduler.c:504 */
+	for (int k = 0; k < GPUHASH_INDEX_SLOTS; k++) ix->slot[k].busy = 0;
+	if (e != cudaSuccess) return (int)e;
+	return cycle_error(ix);
+}
+
+/* mega_scheduler.c:393-502 for all workers at once: one descriptor upload, ONE launch (zero-copy), one event.
+ * Staged mode (pageable or pinned host buffers copied through the per-worker device buffers): the copies of all workers,
+ * the launch and the result copies go on the slot's stream; the staging buffers exist once per worker, so staged cycles
+ * run one after the other (each waits for the previous slot's event). */
+extern "C" int gpuhash_index_submit_all(gpuhash_index_t *ix, const gpuhash_batch_t *batches_h, int num_batches)
+{
+	if (!ix || !batches_h || num_batches < 1 || num_batches > ix->workers) return -1;
+	for (int w = 0; w < num_batches; w++)
+		if (batches_h[w].n_search > ix->max_search || batches_h[w].n_delete > ix->max_delete || batches_h[w].n_insert > ix->max_insert) return -1;
+	const unsigned k = ix->next_slot % GPUHASH_INDEX_SLOTS;
+	struct cycle_slot *c = &ix->slot[k];
+	cudaError_t e;
+	if (c->busy && (e = cudaEventSynchronize(c->done)) != cudaSuccess) return -(int)e - 16;   /* descriptor mirror and workspace still in use */
+	c->busy = 0;
+	cudaStream_t s = c->stream;
+	gpuhash_stats_t *st = ix->stats_on ? ix->stats_d : NULL;
+	const size_t out_bytes = ix->compact ? 4 : 8;
+	if (ix->zero_copy) {
+		memcpy(c->desc_h, batches_h, sizeof(gpuhash_batch_t) * (size_t)num_batches);
+	} else {
+		const struct cycle_slot *prev = &ix->slot[(k + GPUHASH_INDEX_SLOTS - 1) % GPUHASH_INDEX_SLOTS];
+		if (prev->busy && (e = cudaStreamWaitEvent(s, prev->done, 0)) != cudaSuccess) return -(int)e - 16;
+		for (int w = 0; w < num_batches; w++) {
+			const gpuhash_batch_t *b = &batches_h[w];
+			gpuhash_batch_t *d = &c->desc_h[w];
+			memset(d, 0, sizeof *d);
+			d->n_search = b->n_search; d->n_delete = b->n_delete; d->n_insert = b->n_insert;
+			d->search_in = ix->search_in_d[w]; d->search_out = ix->search_out_d[w];
+			d->delete_in = ix->delete_in_d[w]; d->insert_in = ix->insert_in_d[w];
+			if (b->n_search && (e = cudaMemcpyAsync(ix->search_in_d[w], b->search_in, (size_t)b->n_search * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return -(int)e - 16;
+			if (b->n_delete && (e = cudaMemcpyAsync(ix->delete_in_d[w], b->delete_in, (size_t)b->n_delete * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return -(int)e - 16;
+			if (b->n_insert && (e = cudaMemcpyAsync(ix->insert_in_d[w], b->insert_in, (size_t)b->n_insert * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return -(int)e - 16;
+		}
+	}
+	if ((e = cudaMemcpyAsync(c->desc_d, c->desc_h, sizeof(gpuhash_batch_t) * (size_t)num_batches, cudaMemcpyHostToDevice, s)) != cudaSuccess) return -(int)e - 16;
+	int rc = gpuhash_cycle_multi_ex(&ix->geom, ix->table, c->desc_h, c->desc_d, num_batches, ix->compact, c->ws_d, st, s);
+	if (rc) return rc < 0 ? rc : -rc - 16;
+	if (!ix->zero_copy)
+		for (int w = 0; w < num_batches; w++)
+			if (batches_h[w].n_search && (e = cudaMemcpyAsync(batches_h[w].search_out, ix->search_out_d[w], (size_t)batches_h[w].n_search * out_bytes,
+					cudaMemcpyDeviceToHost, s)) != cudaSuccess) return -(int)e - 16;
+	if ((e = cudaEventRecord(c->done, s)) != cudaSuccess) return -(int)e - 16;
+	c->busy = 1;
+	ix->next_slot++;
+	return (int)k;
+}
+
+extern "C" int gpuhash_index_wait(gpuhash_index_t *ix, int ticket)
+{
+	if (!ix || ticket < 0 || ticket >= GPUHASH_INDEX_SLOTS) return -1;
+	struct cycle_slot *c = &ix->slot[ticket];
+	if (c->busy) {
+		cudaError_t e = cudaEventSynchronize(c->done);
+		c->busy = 0;
+		if (e != cudaSuccess) return (int)e;
+	}
+	return cycle_error(ix);
 }
 
 /* ------------------------------------------------------------------ timed loops */
@@ -243,7 +345,7 @@ static int issue_resident(const gpuhash_geom_t *g, void *table_d,
 		int rc;
 		if (tune.fused_cycle && n_search && n_insert) {
 			if ((rc = gpuhash_cycle_ex(g, table_d, search_d + (size_t)i * n_search * 8, n_search, out_d + (size_t)i * n_search * 8,
-					NULL, 0, insert_d + (size_t)i * n_insert * 12, n_insert, NULL, NULL, 0, NULL, s)) != 0) return rc;
+					NULL, 0, insert_d + (size_t)i * n_insert * 12, n_insert, NULL, NULL, 0, NULL, s)) != 0) return rc;   /* pool workspace: direct calls or ONE replayed graph at a time */
 			continue;
 		}
 		if (n_search && (rc = gpuhash_search_ex(g, search_d + (size_t)i * n_search * 8, out_d + (size_t)i * n_search * 8,
@@ -369,4 +471,125 @@ extern "C" int gpuhash_bench_e2e(gpuhash_index_t *ix,
 	res->d2h_bytes = (unsigned long long)steps * n_search * (ix->compact ? 4 : 8);
 	if (rc != 0) return rc;
 	return (int)e;
+}
+
+/* ------------------------------------------------------------------ whole cycles: one launch per step */
+
+#include <time.h>
+static double wall_ms_now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+/* `steps` scheduler cycles, each ONE launch (gpuhash_cycle_multi_ex) over `batches` worker batches resident in device
+ * memory: batch b of step i is batch number i * batches + b of search_d / out_d / insert_d (n_search selem_t, 2 n_search
+ * loc_t, n_insert ielem_t each).  Steps go round-robin over `streams` (1..4) streams, each with its own workspace: with
+ * one stream the cycles run strictly one after the other, like the reference's (one cudaDeviceSynchronize per cycle,
+ * mega_scheduler.c:504); with two the tail of a cycle overlaps the head of the next, which its triple-buffered batches
+ * allow (mega_batch.h:74-82).  Descriptor tables are uploaded before the timed region; CUDA events around the launches. */
+extern "C" int gpuhash_bench_cycles(const gpuhash_geom_t *g, void *table_d,
+		const void *search_d, size_t n_search, void *out_d,
+		const void *insert_d, size_t n_insert,
+		int batches, int steps, int streams, gpuhash_bench_result_t *res)
+{
+	if (!g || !res || steps < 1 || batches < 1 || batches > GPUHASH_MAX_BATCHES || streams < 1 || streams > 4) return -1;
+	if (gpuhash_init_device() != 0) return -1;
+	memset(res, 0, sizeof *res);
+	const size_t nd = (size_t)steps * (size_t)batches;
+	gpuhash_batch_t *dh = (gpuhash_batch_t *)calloc(nd, sizeof *dh), *dd = NULL;
+	if (!dh) return -1;
+	for (size_t k = 0; k < nd; k++) {
+		dh[k].search_in = n_search ? (const char *)search_d + k * n_search * 8 : NULL;
+		dh[k].search_out = n_search ? (char *)out_d + k * n_search * 8 : NULL;
+		dh[k].insert_in = n_insert ? (const char *)insert_d + k * n_insert * 12 : NULL;
+		dh[k].n_search = (uint32_t)n_search; dh[k].n_insert = (uint32_t)n_insert;
+	}
+	cudaStream_t st[4] = {0}, main_s = NULL;
+	cudaEvent_t ev_start = NULL, ev_stop = NULL, ev_done[4] = {0};
+	void *ws[4] = {0};
+	const size_t wsb = gpuhash_cycle_workspace_bytes(batches);
+	cudaError_t e = cudaMalloc((void **)&dd, nd * sizeof *dd);
+	if (e == cudaSuccess) e = cudaMemcpy(dd, dh, nd * sizeof *dd, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main_s, cudaStreamNonBlocking);
+	for (int k = 0; e == cudaSuccess && k < streams; k++) {
+		e = cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaMalloc(&ws[k], wsb);
+		if (e == cudaSuccess) e = cudaMemset(ws[k], 0, wsb);
+	}
+	if (e == cudaSuccess) e = cudaEventCreate(&ev_start);
+	if (e == cudaSuccess) e = cudaEventCreate(&ev_stop);
+	int rc = 0;
+	if (e == cudaSuccess) {
+		cudaDeviceSynchronize();
+		cudaEventRecord(ev_start, main_s);
+		for (int k = 0; k < streams; k++) cudaStreamWaitEvent(st[k], ev_start, 0);
+		for (int i = 0; i < steps && rc == 0; i++)
+			rc = gpuhash_cycle_multi_ex(g, table_d, dh + (size_t)i * batches, dd + (size_t)i * batches, batches, 0, ws[i % streams], NULL, st[i % streams]);
+		for (int k = 0; k < streams; k++) { cudaEventRecord(ev_done[k], st[k]); cudaStreamWaitEvent(main_s, ev_done[k], 0); }
+		cudaEventRecord(ev_stop, main_s);
+		e = cudaEventSynchronize(ev_stop);
+		if (e == cudaSuccess && rc == 0) cudaEventElapsedTime(&res->total_ms, ev_start, ev_stop);
+	}
+	cudaDeviceSynchronize();
+	if (rc == 0 && gpuhash_cycle_error(1)) rc = -3;
+	for (int k = 0; k < streams; k++) { if (st[k]) cudaStreamDestroy(st[k]); if (ev_done[k]) cudaEventDestroy(ev_done[k]); cudaFree(ws[k]); }
+	if (main_s) cudaStreamDestroy(main_s);
+	if (ev_start) cudaEventDestroy(ev_start);
+	if (ev_stop) cudaEventDestroy(ev_stop);
+	cudaFree(dd); free(dh);
+	res->launches = (unsigned long long)steps;
+	res->search_ops = (unsigned long long)nd * n_search;
+	res->insert_ops = (unsigned long long)nd * n_insert;
+	if (rc != 0) return rc;
+	return (int)e;
+}
+
+/* The same cycles end to end through the host-buffer call a scheduler makes: gpuhash_index_submit_all per step (pinned
+ * host batches in, results back in pinned host memory), at most `depth` (1..GPUHASH_INDEX_SLOTS) cycles in flight,
+ * gpuhash_index_wait before a slot is reused and for everything at the end.  total_ms is the HOST'S WALL CLOCK from the
+ * first submit to the return of the last wait: launch latency, descriptor uploads and synchronisation included.
+ * Batch b of step i is batch (i * batches + b) % host_batches of the pinned arrays. */
+extern "C" int gpuhash_bench_e2e_cycles(gpuhash_index_t *ix,
+		const void *search_h, size_t n_search, void *out_h,
+		const void *insert_h, size_t n_insert,
+		int batches, size_t host_batches, int steps, int depth, gpuhash_bench_result_t *res)
+{
+	if (!ix || !res || steps < 1 || batches < 1 || batches > ix->workers || depth < 1 || depth > GPUHASH_INDEX_SLOTS) return -1;
+	if (host_batches < (size_t)batches * (size_t)depth) return -1;
+	memset(res, 0, sizeof *res);
+	const size_t ob = ix->compact ? 4 : 8;
+	gpuhash_batch_t *d = (gpuhash_batch_t *)calloc((size_t)batches, sizeof *d);
+	if (!d) return -1;
+	int tickets[GPUHASH_INDEX_SLOTS];
+	int rc = 0;
+	cudaDeviceSynchronize();
+	const double t0 = wall_ms_now();
+	for (int i = 0; i < steps && rc == 0; i++) {
+		for (int b = 0; b < batches; b++) {
+			const size_t k = ((size_t)i * batches + b) % host_batches;
+			d[b].search_in = n_search ? (const char *)search_h + k * n_search * 8 : NULL;
+			d[b].search_out = n_search ? (char *)out_h + k * n_search * ob : NULL;
+			d[b].insert_in = n_insert ? (const char *)insert_h + k * n_insert * 12 : NULL;
+			d[b].n_search = (uint32_t)n_search; d[b].n_insert = (uint32_t)n_insert;
+		}
+		if (i >= depth) rc = gpuhash_index_wait(ix, tickets[i % depth]);       /* the scheduler hands that batch on before reusing the slot */
+		if (rc) break;
+		const int t = gpuhash_index_submit_all(ix, d, batches);
+		if (t < 0) { rc = t; break; }
+		tickets[i % depth] = t;
+	}
+	for (int i = steps > depth ? steps - depth : 0; i < steps && rc == 0; i++) rc = gpuhash_index_wait(ix, tickets[i % depth]);
+	const double t1 = wall_ms_now();
+	cudaDeviceSynchronize();
+	free(d);
+	res->total_ms = (float)(t1 - t0);
+	res->launches = (unsigned long long)steps;
+	res->search_ops = (unsigned long long)steps * batches * n_search;
+	res->insert_ops = (unsigned long long)steps * batches * n_insert;
+	res->h2d_bytes = (unsigned long long)steps * batches * (n_search * 8 + n_insert * 12);
+	res->d2h_bytes = (unsigned long long)steps * batches * n_search * ob;
+	return rc;
 }

@@ -1154,133 +1154,234 @@ fold_keys_kernel(const unsigned char* __restrict__ keys, size_t stride, uint32_t
 	}
 }
 
-/* ---- one launch per scheduler cycle: search -> delete -> insert ---- */
+/* ---- one launch per scheduler cycle, all workers: search -> delete -> insert per worker ---- */
 
-// The reference issues three launches per worker and cycle, stream-ordered search -> delete -> insert
-// (mega_scheduler.c:392-502), and declares a fused gpu_delete_insert it never defines (libgpuhash.h:53-62).
-// Here the whole cycle of one worker is ONE launch.  CTAs [0, Bs) search, [Bs, Bs+Bd) delete, the rest insert;
-// a delete CTA starts only when all Bs search CTAs have finished, an insert CTA only when all search and delete
-// CTAs have (counters in global memory).  CTAs of a 1-D grid are dispatched in index order, so when a waiting CTA
-// is resident every CTA it waits for has been dispatched already and none of them waits on anything: no
-// deadlock.  Results equal the three stream-ordered launches; what is saved is two launches per batch, which at
-// 64 K requests per batch is more than the lookups themselves cost.
-struct CycleArgs {
-	const uint2* search_in; uint2* search_out; unsigned long long n_search;
-	const uint32_t* delete_in; unsigned long long n_delete;
-	const uint32_t* insert_in; unsigned long long n_insert;          // flat insert batch, or
-	const uint32_t* const* blk_input; const int* blk_elem_num; int num_blks;   // ... segments with device-side counts
-	unsigned int search_ctas, delete_ctas, insert_ctas;
-	unsigned int* counters;                                           // [4], zero on entry, zero again on exit
+// The reference's cycle walks every worker's batch -- H2D, search launch, D2H, then the delete and the insert launch on
+// the worker's stream -- and synchronises ONCE (mega_scheduler.c:393-420, 440-502, 504); it also declares a fused
+// gpu_delete_insert it never defines (libgpuhash.h:53-62).  Here the whole cycle of all W workers is ONE launch over a
+// table of W batch descriptors.  Work is cut into tiles of 64 requests; the tile index space is phase-major: all search
+// tiles (worker 0..W-1), then all delete tiles, then all insert tiles.  Every WARP takes its next tile with an atomic
+// ticket, so a tile is only ever held by a warp that is running, and the only things a tile waits for -- the search
+// tiles of its own worker (delete), the search and delete tiles of its own worker (insert) -- have smaller indices:
+// they are held by running warps or finished.  No assumption about the order in which CTAs are dispatched, about how
+// many are resident, or about other kernels sharing the GPU (the first version ordered the phases by blockIdx).
+// Per worker the order is the reference's in-stream order search -> delete -> insert; workers are unordered against
+// each other, like the reference's streams.  Waits are bounded (timeout -> error word, the warp goes on).
+//   workspace `ws` (caller-owned, zero before the first launch, left zero by every launch):
+//     [0] tile ticket  [1] CTAs finished  [2] error (sticky, never cleared by the kernel)  [3] -
+//     [4 + 2w] search tiles of worker w finished   [5 + 2w] delete tiles of worker w finished
+struct BatchDesc {                                        // == gpuhash_batch_t (gpuhash_ex.h)
+	const void* search_in; void* search_out;              // selem_t[n_search]; loc_t[2 n_search] (compact: loc_t[n_search])
+	const void* delete_in; const void* insert_in;         // delem_t[n_delete]; ielem_t[n_insert]
+	uint32_t n_search, n_delete, n_insert, reserved;
+};
+static_assert(sizeof(BatchDesc) == 48, "gpuhash_batch_t");
+
+constexpr int kMaxBatches = 128;                          // descriptors per launch
+constexpr int kMaxSegs = 64;                              // legacy insert segments (device-side counts) per launch
+constexpr int kMaxSpans = 3 * kMaxBatches + kMaxSegs;
+
+struct MultiArgs {
+	const BatchDesc* descs; int W;                        // device-readable descriptor table, or (descs == NULL, W == 1) d0
+	BatchDesc d0;
+	const uint32_t* const* seg_ptrs; const int* seg_counts; int num_segs;   // extra insert spans of worker 0 (gpu_hash_insert's
+	                                                                        // blk_input / blk_elem_num: both live in device memory)
+	uint32_t* ws;
+	volatile uint32_t* err_host;                          // optional pinned word the host polls after its sync
+	unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ void cycle_wait(const unsigned int* c, unsigned int target)
+struct SpanTable {                                        // views into dynamic shared memory, built by every CTA
+	const void** in;                                      // [spans]
+	void** out;                                           // [W]
+	uint32_t* n;                                          // [spans]
+	uint32_t* first;                                      // [spans + 1]: first tile of span s; first[spans] = all tiles
+	int spans, W;
+};
+__host__ __device__ inline size_t span_table_bytes(int W, int segs)
 {
+	const size_t spans = 3 * (size_t)W + (size_t)segs;
+	return spans * 8 + (size_t)W * 8 + spans * 4 + (spans + 1) * 4 + 16;
+}
+
+__device__ __forceinline__ uint32_t tiles_of_search(const void* in, uint32_t n)
+{
+	if (n == 0) return 0;
+	const uint32_t head = ((uintptr_t)in & 15u) ? 1u : 0u;   // tiles start at the first 16 B-aligned request
+	const uint32_t t = (n - head + kTileReq - 1) / kTileReq;
+	return t ? t : 1u;                                    // a lone misaligned request still needs someone to serve it
+}
+
+__device__ __forceinline__ void span_table_build(SpanTable& S, unsigned char* smem, const MultiArgs& a)
+{
+	const int W = a.W, segs = a.num_segs;
+	const int spans = 3 * W + segs;
+	S.in = (const void**)smem; S.out = (void**)(smem + (size_t)spans * 8);
+	S.n = (uint32_t*)(smem + (size_t)spans * 8 + (size_t)W * 8); S.first = S.n + spans;
+	S.spans = spans; S.W = W;
+	for (int w = threadIdx.x; w < W; w += blockDim.x) {
+		const BatchDesc d = a.descs ? a.descs[w] : a.d0;
+		S.in[w] = d.search_in; S.out[w] = d.search_out; S.n[w] = d.n_search;
+		S.in[W + w] = d.delete_in; S.n[W + w] = d.n_delete;
+		S.in[2 * W + w] = d.insert_in; S.n[2 * W + w] = d.n_insert;
+	}
+	for (int k = threadIdx.x; k < segs; k += blockDim.x) {
+		const int c = a.seg_counts[k];
+		S.in[3 * W + k] = a.seg_ptrs[k]; S.n[3 * W + k] = c > 0 ? (uint32_t)c : 0u;
+	}
+	__syncthreads();
 	if (threadIdx.x == 0) {
-		unsigned int v;
-		do {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
-			if (v < target) __nanosleep(64);
-		} while (v < target);
+		uint32_t acc = 0;
+		for (int s = 0; s < spans; s++) {
+			S.first[s] = acc;
+			acc += s < W ? tiles_of_search(S.in[s], S.n[s]) : (S.n[s] + kTileReq - 1) / kTileReq;
+		}
+		S.first[spans] = acc;
 	}
 	__syncthreads();
 }
 
-template <bool kPairs>
-__global__ void __launch_bounds__(256)
-cycle_kernel(Bucket* table, Geom g, Stats* st, CycleArgs a)
+__device__ __forceinline__ int span_of_tile(const SpanTable& S, uint32_t t)          // largest s with first[s] <= t (t < all tiles)
 {
-	const unsigned int bid = blockIdx.x;
-	int phase;
-	if (bid < a.search_ctas) {                                       // ---- search: every warp walks 64-request tiles (warp_tile_search)
-		phase = 0;
-		const unsigned lane = threadIdx.x & 31u;
-		const uint2* in = a.search_in; uint2* out = a.search_out;
-		const unsigned head = ((uintptr_t)in & 15u) ? 1u : 0u;       // tiles start at the first 16 B-aligned request
-		const bool out_vec = (((uintptr_t)out + 8u * head) & 15u) == 0;
-		const unsigned long long warp = (unsigned long long)bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
-		const unsigned long long warps = (unsigned long long)a.search_ctas * (blockDim.x >> 5);
-		uint32_t h1 = 0, h2 = 0;
-		if (head && warp == 0 && a.n_search) {
-			const uint4 v = warp_tile_load<false>(in, 1u, lane);
-			warp_tile_search<kPairs, false>(table, g, in, out, 1u, false, v, lane, h1, h2);
-		}
-		const uint2* in_a = in + head; uint2* out_a = out + head;
-		const unsigned long long n_a = a.n_search ? a.n_search - head : 0;
-		const unsigned long long tiles = (n_a + kTileReq - 1) / kTileReq;
-		unsigned long long t = warp;
-		uint4 v = make_uint4(0u, 0u, 0u, 0u);
-		if (t < tiles) v = warp_tile_load<false>(in_a + t * kTileReq, (uint32_t)min((unsigned long long)kTileReq, n_a - t * kTileReq), lane);
-		for (; t < tiles; t += warps) {
-			const uint32_t valid = (uint32_t)min((unsigned long long)kTileReq, n_a - t * kTileReq);
-			const unsigned long long tn = t + warps;
-			uint4 vn = make_uint4(0u, 0u, 0u, 0u);
-			if (tn < tiles) vn = warp_tile_load<false>(in_a + tn * kTileReq, (uint32_t)min((unsigned long long)kTileReq, n_a - tn * kTileReq), lane);
-			warp_tile_search<kPairs, false>(table, g, in_a + t * kTileReq, out_a + t * kTileReq, valid, out_vec, v, lane, h1, h2);
-			v = vn;
-		}
-		if (st) {
-			if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
-			if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
-		}
-	} else if (bid < a.search_ctas + a.delete_ctas) {                // ---- delete, after every search
-		phase = 1;
-		cycle_wait(a.counters + 0, a.search_ctas);
-		const unsigned long long stride = (unsigned long long)a.delete_ctas * blockDim.x;
-		if (kPairs) {                                                // two lanes per request
-			const unsigned long long n_up = (a.n_delete + 15ULL) & ~15ULL;
-			for (unsigned long long i = ((unsigned long long)(bid - a.search_ctas) * blockDim.x + threadIdx.x) >> 1; i < n_up; i += stride >> 1) {
-				const bool have = i < a.n_delete;
-				uint32_t x = 0, y = 0, w = 0;
-				if (have) { x = ld_stream_u32(a.delete_in + 3 * i); y = ld_stream_u32(a.delete_in + 3 * i + 1); w = ld_stream_u32(a.delete_in + 3 * i + 2); }
-				const int z = delete_pair(table, g, have, x, y, w, threadIdx.x & 31u);
-				if (st && z && (threadIdx.x & 1u) == 0) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
+	int lo = 0, hi = S.spans;                             // invariant: first[lo] <= t < first[hi]
+	while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.first[mid] <= t) lo = mid; else hi = mid; }
+	return lo;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p)
+{
+	uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+// whole warp: wait until *c >= target (lane 0 polls; everyone leaves together)
+__device__ __forceinline__ void tiles_wait(const uint32_t* c, uint32_t target, const MultiArgs& a, unsigned lane)
+{
+	if (target == 0) return;
+	if (lane == 0 && ld_acquire_gpu_u32(c) < target) {
+		unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+		for (;;) {
+			__nanosleep(128);
+			if (ld_acquire_gpu_u32(c) >= target) break;
+			unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+			if (t1 - t0 > a.timeout_ns) {                // never seen in practice; a hung box is worse than a flagged batch
+				atomicExch(a.ws + 2, 1u);
+				if (a.err_host) *a.err_host = 1u;
+				break;
 			}
-		} else
-		for (unsigned long long i = (unsigned long long)(bid - a.search_ctas) * blockDim.x + threadIdx.x; i < a.n_delete; i += stride) {
-			int z = delete_one<kPairs>(table, g, ld_stream_u32(a.delete_in + 3 * i), ld_stream_u32(a.delete_in + 3 * i + 1),
-					ld_stream_u32(a.delete_in + 3 * i + 2));
-			if (st && z) { atomicAdd(&st->del_zeroed, (unsigned long long)z); atomicAdd(&st->del_requests_hit, 1ULL); }
-		}
-	} else {                                                         // ---- insert, after every search and delete
-		phase = 2;
-		cycle_wait(a.counters + 0, a.search_ctas);
-		cycle_wait(a.counters + 1, a.delete_ctas);
-		const unsigned int ib = bid - a.search_ctas - a.delete_ctas;
-		const unsigned long long stride = (unsigned long long)a.insert_ctas * blockDim.x;
-		if (a.blk_input) {
-			unsigned long long base = 0;                             // segments are few (INSERT_BLOCK = 8): walk them
-			for (int k = 0; k < a.num_blks; k++) {
-				const int c = a.blk_elem_num[k];
-				const unsigned long long cnt = c > 0 ? (unsigned long long)c : 0ULL;
-				const uint32_t* p = a.blk_input[k];
-				// element e of the concatenation belongs to thread (e mod stride)
-				unsigned long long first = (unsigned long long)ib * blockDim.x + threadIdx.x;
-				first = first >= base % stride ? first - base % stride : first + stride - base % stride;
-				for (unsigned long long e = first; e < cnt; e += stride)
-					insert_one<kPairs>(table, g, ld_stream_u32(p + 3 * e), ld_stream_u32(p + 3 * e + 1), ld_stream_u32(p + 3 * e + 2), st);
-				base += cnt;
-			}
-		} else if (kPairs) {                                         // two lanes per request
-			const unsigned long long n_up = (a.n_insert + 15ULL) & ~15ULL;
-			for (unsigned long long i = ((unsigned long long)ib * blockDim.x + threadIdx.x) >> 1; i < n_up; i += stride >> 1) {
-				const bool have = i < a.n_insert;
-				uint32_t x = 0, y = 0, w = 0;
-				if (have) { x = ld_stream_u32(a.insert_in + 3 * i); y = ld_stream_u32(a.insert_in + 3 * i + 1); w = ld_stream_u32(a.insert_in + 3 * i + 2); }
-				insert_pair(table, g, have, x, y, w, st, threadIdx.x & 31u);
-			}
-		} else {
-			for (unsigned long long i = (unsigned long long)ib * blockDim.x + threadIdx.x; i < a.n_insert; i += stride)
-				insert_one<kPairs>(table, g, ld_stream_u32(a.insert_in + 3 * i), ld_stream_u32(a.insert_in + 3 * i + 1),
-						ld_stream_u32(a.insert_in + 3 * i + 2), st);
 		}
 	}
-	// ---- this CTA is done: count it; the last CTA of the launch clears the counters for their next user
+	__syncwarp();
+}
+
+#ifndef GH_CYCLE_MIN_CTAS
+#define GH_CYCLE_MIN_CTAS 3          /* 80 registers, no spills; 4 forces 64 registers and spills 40-56 B per thread */
+#endif
+template <bool kPairs, bool kCompact>
+__global__ void __launch_bounds__(256, GH_CYCLE_MIN_CTAS)
+cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
+{
+	extern __shared__ __align__(16) unsigned char span_smem[];
+	SpanTable S;                                          // the views live in registers, the arrays in shared memory
+	constexpr size_t kOutBytes = kCompact ? 4 : 8;
+	pdl_enter();
+	span_table_build(S, span_smem, a);
+	const unsigned lane = threadIdx.x & 31u;
+	const uint32_t total = S.first[S.spans];
+	const int W = S.W;
+	uint32_t h1 = 0, h2 = 0;
+
+	// Tickets are taken two tiles ahead of their use: the atomic issued at the top of an iteration is only read
+	// (shuffled out of lane 0) at its bottom, and the requests of the NEXT tile are already in flight while this
+	// one is probed -- neither latency is on the warp's critical path.
+	auto claim_issue = [&]() -> uint32_t { return lane == 0 ? atomicAdd(a.ws + 0, 1u) : 0u; };
+	// requests of a search tile (this lane's 16 B); nothing for other tiles
+	auto prefetch = [&](uint32_t t, int s) -> uint4 {
+		if (t >= total || s >= W) return make_uint4(0u, 0u, 0u, 0u);
+		const uint2* in = (const uint2*)S.in[s];
+		const uint32_t head = ((uintptr_t)in & 15u) ? 1u : 0u;
+		const uint32_t n_a = S.n[s] - head, r0 = (t - S.first[s]) * kTileReq;
+		return warp_tile_load<false>(in + head + r0, min((uint32_t)kTileReq, n_a - min(n_a, r0)), lane);
+	};
+
+	uint32_t cur = __shfl_sync(0xffffffffu, claim_issue(), 0);
+	uint32_t nxt = __shfl_sync(0xffffffffu, claim_issue(), 0);
+	int s_cur = cur < total ? span_of_tile(S, cur) : 0;
+	uint4 v = prefetch(cur, s_cur);
+	while (cur < total) {
+		const uint32_t raw_nn = claim_issue();
+		const int s_nxt = nxt < total ? span_of_tile(S, nxt) : 0;
+		const uint4 vn = prefetch(nxt, s_nxt);            // in flight while this tile is probed
+		const int s = s_cur;
+		const uint32_t lt = cur - S.first[s];             // tile inside its span
+		if (s < W) {                                      // ---- search
+			const uint2* in = (const uint2*)S.in[s]; char* out = (char*)S.out[s];
+			const uint32_t n = S.n[s];
+			const uint32_t head = ((uintptr_t)in & 15u) ? 1u : 0u;
+			const bool out_vec = (((uintptr_t)out + kOutBytes * head) & (kCompact ? 7u : 15u)) == 0;
+			if (head && lt == 0) {                        // the request in front of the first aligned tile
+				const uint4 v0 = warp_tile_load<false>(in, 1u, lane);
+				warp_tile_search<kPairs, false, kCompact>(table, g, in, out, 1u, false, v0, lane, h1, h2);
+			}
+			const uint32_t n_a = n - head, r0 = lt * kTileReq;
+			const uint32_t valid = min((uint32_t)kTileReq, n_a - min(n_a, r0));
+			if (valid)
+				warp_tile_search<kPairs, false, kCompact>(table, g, in + head + r0, out + kOutBytes * (head + (size_t)r0), valid, out_vec, v, lane, h1, h2);
+			__syncwarp();
+			if (lane == 0) { __threadfence(); atomicAdd(a.ws + 4 + 2 * s, 1u); }
+		} else {                                          // ---- delete / insert
+			const bool is_delete = s < 2 * W;
+			const int w = is_delete ? s - W : (s < 3 * W ? s - 2 * W : 0);       // segments belong to worker 0
+			tiles_wait(a.ws + 4 + 2 * w, S.first[w + 1] - S.first[w], a, lane);
+			if (!is_delete) tiles_wait(a.ws + 5 + 2 * w, S.first[W + w + 1] - S.first[W + w], a, lane);
+			const uint32_t* in = (const uint32_t*)S.in[s];
+			const uint32_t n = S.n[s], r0 = lt * kTileReq;
+			if (kPairs) {                                 // two lanes per request: 16 requests per round
+#pragma unroll 1
+				for (uint32_t r = 0; r < (uint32_t)kTileReq; r += 16) {
+					if (r0 + r >= n) break;               // warp-uniform
+					const uint32_t i = r0 + r + (lane >> 1);
+					const bool have = i < n;
+					uint32_t x = 0, y = 0, z = 0;
+					if (have) { x = ld_stream_u32(in + 3 * (size_t)i); y = ld_stream_u32(in + 3 * (size_t)i + 1); z = ld_stream_u32(in + 3 * (size_t)i + 2); }
+					if (is_delete) {
+						const int zc = delete_pair(table, g, have, x, y, z, lane);
+						if (st && zc && (lane & 1u) == 0) { atomicAdd(&st->del_zeroed, (unsigned long long)zc); atomicAdd(&st->del_requests_hit, 1ULL); }
+					} else {
+						insert_pair(table, g, have, x, y, z, st, lane);
+					}
+				}
+			} else {
+#pragma unroll 1
+				for (uint32_t r = 0; r < (uint32_t)kTileReq; r += 32) {
+					const uint32_t i = r0 + r + lane;
+					if (i < n) {
+						const uint32_t x = ld_stream_u32(in + 3 * (size_t)i), y = ld_stream_u32(in + 3 * (size_t)i + 1), z = ld_stream_u32(in + 3 * (size_t)i + 2);
+						if (is_delete) {
+							const int zc = delete_one<false>(table, g, x, y, z);
+							if (st && zc) { atomicAdd(&st->del_zeroed, (unsigned long long)zc); atomicAdd(&st->del_requests_hit, 1ULL); }
+						} else {
+							insert_one<false>(table, g, x, y, z, st);
+						}
+					}
+				}
+			}
+			__syncwarp();
+			if (is_delete && lane == 0) { __threadfence(); atomicAdd(a.ws + 5 + 2 * w, 1u); }
+		}
+		cur = nxt; s_cur = s_nxt; v = vn;
+		nxt = __shfl_sync(0xffffffffu, raw_nn, 0);
+	}
+	if (st) {                                             // every quad's first lane counted its own hits
+		if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
+		if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
+	}
+	// ---- this CTA is done; the last one leaves the workspace zero for its next user (the error word stays)
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence();
-		atomicAdd(a.counters + phase, 1u);
-		if (atomicAdd(a.counters + 3, 1u) == gridDim.x - 1) {
-			a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0;
+		if (atomicAdd(a.ws + 1, 1u) == gridDim.x - 1) {
+			a.ws[0] = 0; a.ws[1] = 0;
+			for (int w = 0; w < W; w++) { a.ws[4 + 2 * w] = 0; a.ws[5 + 2 * w] = 0; }
 			__threadfence();
 		}
 	}

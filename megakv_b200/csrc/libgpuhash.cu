@@ -398,27 +398,184 @@ extern "C" int gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, uns
 	return (int)cudaGetLastError();
 }
 
-/* One launch for a whole scheduler cycle of one worker: searches, then deletes, then inserts (flat batch with a
- * host-known count, or -- blk_input_d != NULL -- segments with device-side counts).  Same results as
- * gpuhash_search_ex, gpuhash_delete_ex, gpuhash_insert_*_ex issued in that order on one stream. */
+/* ---- one launch per scheduler cycle (gh::cycle_multi_kernel) ----
+ * Workspaces: the kernel orders its phases through a few counters in device memory that must be zero at launch and are
+ * left zero at exit, so one workspace serves one launch at a time.  Callers that replay launches from CUDA graphs, or
+ * issue from several host threads, own their workspaces (gpuhash_cycle_multi_ex; gpuhash_index_* keeps one per worker
+ * stream and one per submit_all slot).  The stateless entry points (gpuhash_cycle_ex, the legacy gpu_delete_insert) take a
+ * slot from a per-device pool by an atomic round-robin counter: a slot is reused GH_CYCLE_SLOTS launches later. */
 #define GH_CYCLE_SLOTS 4096
-static unsigned int *g_cycle_counters[64];        /* per device: GH_CYCLE_SLOTS x 4 words, zero */
+#define GH_POOL_WS_WORDS 8                        /* ticket, finished, error, -, and one worker's two phase counters */
+static unsigned int *g_cycle_pool[64];            /* per device: GH_CYCLE_SLOTS x GH_POOL_WS_WORDS words, zero */
 static unsigned int g_cycle_next[64];
+static volatile unsigned int *g_cycle_err[64];    /* per device: pinned word a cycle kernel sets when a phase wait timed out */
 
-/* Per-device state of the library (the counter slots of gpuhash_cycle_ex, cached device attributes).  Idempotent. */
+/* Per-device state of the library (the workspace pool, cached device attributes).  Idempotent; synchronises. */
 extern "C" int gpuhash_init_device(void)
 {
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
 	(void)sm_count_now(); (void)l2_bytes_now();
-	if (!g_cycle_counters[dev]) {
+	if (!__atomic_load_n(&g_cycle_pool[dev], __ATOMIC_ACQUIRE)) {
 		unsigned int *p = NULL;
-		cudaError_t e = cudaMalloc((void **)&p, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int));
+		const size_t bytes = (size_t)GH_CYCLE_SLOTS * GH_POOL_WS_WORDS * sizeof(unsigned int);
+		cudaError_t e = cudaMalloc((void **)&p, bytes);
 		if (e != cudaSuccess) return (int)e;
-		if ((e = cudaMemset(p, 0, GH_CYCLE_SLOTS * 4 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
-		g_cycle_counters[dev] = p;
+		/* cudaMemset on device memory is asynchronous to the host and the library's streams are non-blocking:
+		 * nothing may be launched on the pool before the fill has finished */
+		if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) { cudaFree(p); return (int)e; }
+		unsigned int *err = NULL;
+		if ((e = cudaHostAlloc((void **)&err, 64, cudaHostAllocDefault)) != cudaSuccess) { cudaFree(p); return (int)e; }
+		*err = 0;
+		unsigned int *expect = NULL;
+		if (__atomic_compare_exchange_n(&g_cycle_pool[dev], &expect, p, 0, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) g_cycle_err[dev] = err;
+		else { cudaFree(p); cudaFreeHost(err); }                       /* another thread won */
 	}
 	return 0;
+}
+
+/* 1 if a phase wait inside a one-launch cycle on the current device has timed out since the last reset (the batch that
+ * was running is suspect); read after synchronising.  reset != 0 clears it. */
+extern "C" int gpuhash_cycle_error(int reset)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_cycle_err[dev]) return 0;
+	const int v = *g_cycle_err[dev] != 0;
+	if (v && reset) *g_cycle_err[dev] = 0;
+	return v;
+}
+
+extern "C" size_t gpuhash_cycle_workspace_bytes(int max_batches)
+{
+	if (max_batches < 1) max_batches = 1;
+	return (((size_t)4 + 2 * (size_t)max_batches) * sizeof(unsigned int) + 63) & ~(size_t)63;
+}
+
+static unsigned long long cycle_timeout_ns(void)
+{
+	static unsigned long long v = 0;
+	if (!v) { const char *e = getenv("GPUHASH_CYCLE_TIMEOUT_MS"); long ms = e && *e ? atol(e) : 0; v = (unsigned long long)(ms > 0 ? ms : 10000) * 1000000ULL; }
+	return v;
+}
+
+/* shape + launch shared by every entry point of the one-launch cycle.  total_tiles: from host-side counts (0 = unknown:
+ * full persistent grid) */
+static int launch_cycle_multi(const gpuhash_geom_t *g, void *table_d, gh::MultiArgs &a, size_t total_tiles, int compact,
+		gpuhash_stats_t *stats_d, cudaStream_t s)
+{
+	const size_t sms = (size_t)sm_count_now();
+	/* small cycles (a lone 64 K batch is ~1000 tiles) take 2-warp CTAs so that they still reach every SM */
+	const unsigned threads = total_tiles && total_tiles <= sms * 16 ? 64u : 256u;
+	const size_t wpc = threads / 32;
+	size_t blocks = sms * (2048 / threads);
+	if (total_tiles) { const size_t need = (total_tiles + wpc - 1) / wpc; if (need < blocks) blocks = need; }
+	if (blocks == 0) blocks = 1;
+	const size_t smem = gh::span_table_bytes(a.W, a.num_segs);
+	a.timeout_ns = cycle_timeout_ns();
+	{
+		int dev = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+			if (!__atomic_load_n(&g_cycle_pool[dev], __ATOMIC_ACQUIRE)) (void)gpuhash_init_device();   /* (fails inside a stream capture: */
+			a.err_host = g_cycle_err[dev];                                                              /*  then errors stay in ws[2])    */
+		}
+	}
+	gh::Geom gg = to_geom(g);
+	gh::Bucket *t = (gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
+	const bool pairs = gg.layout == gh::kLayoutPairs;
+	if (pairs && !compact)      gh::cycle_multi_kernel<true, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
+	else if (pairs)             gh::cycle_multi_kernel<true, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
+	else if (!compact)          gh::cycle_multi_kernel<false, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
+	else                        gh::cycle_multi_kernel<false, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
+	return (int)cudaGetLastError();
+}
+
+static size_t tiles_of_batch(const gpuhash_batch_t *b)
+{
+	size_t t = 0;
+	if (b->n_search) { const size_t head = ((uintptr_t)b->search_in & 15u) ? 1 : 0; const size_t k = (b->n_search - head + gh::kTileReq - 1) / gh::kTileReq; t += k ? k : 1; }
+	t += ((size_t)b->n_delete + gh::kTileReq - 1) / gh::kTileReq + ((size_t)b->n_insert + gh::kTileReq - 1) / gh::kTileReq;
+	return t;
+}
+
+static int batch_ok(const gpuhash_batch_t *b, int compact)
+{
+	if ((b->n_search && (!b->search_in || !b->search_out)) || (b->n_delete && !b->delete_in) || (b->n_insert && !b->insert_in)) return 0;
+	if (((uintptr_t)b->search_in & 7u) || ((uintptr_t)b->search_out & (compact ? 3u : 7u)) || ((uintptr_t)b->delete_in & 3u) || ((uintptr_t)b->insert_in & 3u)) return 0;
+	return 1;
+}
+
+/* The whole cycle of num_batches workers in ONE launch: per batch search -> delete -> insert (the reference's in-stream
+ * order, mega_scheduler.c:392-502), batches unordered against each other (its streams).  batches_d: the descriptor table
+ * where the DEVICE reads it (device memory; every CTA reads it, so not pinned host memory); batches_h: the same table on
+ * the host, used to size the grid (NULL: full persistent grid).  workspace_d: gpuhash_cycle_workspace_bytes(num_batches)
+ * zeroed bytes owned by the caller, one launch at a time.  compact != 0: one result word per search (mega_send.c:411-414). */
+extern "C" int gpuhash_cycle_multi_ex(const gpuhash_geom_t *g, void *table_d, const gpuhash_batch_t *batches_h,
+		const gpuhash_batch_t *batches_d, int num_batches, int compact, void *workspace_d, gpuhash_stats_t *stats_d, void *stream)
+{
+	static_assert(sizeof(gpuhash_batch_t) == sizeof(gh::BatchDesc), "descriptor mirror");
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || !table_d || !batches_d || !workspace_d) return -1;
+	if (num_batches < 1 || num_batches > gh::kMaxBatches) return -1;
+	size_t tiles = 0;
+	if (batches_h) {
+		for (int w = 0; w < num_batches; w++) { if (!batch_ok(&batches_h[w], compact)) return -1; tiles += tiles_of_batch(&batches_h[w]); }
+		if (tiles == 0) return 0;
+	}
+	gh::MultiArgs a; memset(&a, 0, sizeof a);
+	a.descs = (const gh::BatchDesc *)batches_d; a.W = num_batches;
+	a.ws = (uint32_t *)workspace_d;
+	return launch_cycle_multi(g, table_d, a, tiles, compact, stats_d, (cudaStream_t)stream);
+}
+
+/* One launch for a whole scheduler cycle of ONE worker: searches, then deletes, then inserts (flat batch with a
+ * host-known count, or -- blk_input_d != NULL -- segments with device-side counts).  Same results as
+ * gpuhash_search_ex, gpuhash_delete_ex, gpuhash_insert_*_ex issued in that order on one stream.
+ * workspace_d: as gpuhash_cycle_multi_ex (one batch), or NULL = a slot of the per-device pool. */
+extern "C" int gpuhash_cycle_ws_ex(const gpuhash_geom_t *g, void *table_d,
+		const void *selem_d, size_t n_search, void *out_d,
+		const void *delem_d, size_t n_delete,
+		const void *ielem_d, size_t n_insert,
+		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
+		int compact, void *workspace_d, gpuhash_stats_t *stats_d, void *stream)
+{
+	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || !table_d) return -1;
+	if (n_search > 0xffffffffULL || n_delete > 0xffffffffULL || n_insert > 0xffffffffULL) return -1;
+	if (blk_input_d && (!blk_elem_num_d || num_blks < 1 || n_insert)) return -1;
+	gpuhash_batch_t b; memset(&b, 0, sizeof b);
+	b.search_in = selem_d; b.search_out = out_d; b.delete_in = delem_d; b.insert_in = ielem_d;
+	b.n_search = (uint32_t)n_search; b.n_delete = (uint32_t)n_delete; b.n_insert = (uint32_t)n_insert;
+	if (!batch_ok(&b, compact)) return -1;
+	cudaStream_t s = (cudaStream_t)stream;
+	if (blk_input_d && num_blks > gh::kMaxSegs) {
+		/* more segments than the span table holds (the scheduler uses INSERT_BLOCK = 8): the delete and the
+		 * count-independent insert launch, stream-ordered -- same results */
+		int rc = 0;
+		if (n_search && (rc = compact ? gpuhash_search_compact_ex(g, selem_d, out_d, table_d, n_search, stats_d, stream)
+		                              : gpuhash_search_ex(g, selem_d, out_d, table_d, n_search, stats_d, stream)) != 0) return rc;
+		if (n_delete && (rc = gpuhash_delete_ex(g, delem_d, table_d, n_delete, stats_d, 0, stream)) != 0) return rc;
+		return gpuhash_insert_ex(g, table_d, blk_input_d, blk_elem_num_d, num_blks, stats_d, 0, stream);
+	}
+	size_t tiles = tiles_of_batch(&b);
+	if (tiles == 0 && !blk_input_d) return 0;
+	gh::MultiArgs a; memset(&a, 0, sizeof a);
+	a.descs = nullptr; a.W = 1; memcpy(&a.d0, &b, sizeof b);
+	if (blk_input_d) {
+		a.seg_ptrs = (const uint32_t *const *)blk_input_d; a.seg_counts = blk_elem_num_d; a.num_segs = num_blks;
+		/* segment sizes live in device memory (mega_scheduler.c:493-494): assume the server's bound per segment
+		 * (batch_max_insert_job = 4096, mega.c:143) for the grid; the kernel itself reads the real counts */
+		tiles += (size_t)num_blks * (4096 / gh::kTileReq);
+	}
+	if (workspace_d) a.ws = (uint32_t *)workspace_d;
+	else {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+		if (!__atomic_load_n(&g_cycle_pool[dev], __ATOMIC_ACQUIRE)) {      /* first use on this device (not allowed while a stream is   */
+			int rc = gpuhash_init_device();                                /* capturing: gpuhash_index_create and the bench loops call   */
+			if (rc) return rc;                                             /* this up front)                                             */
+		}
+		const unsigned slot = __atomic_fetch_add(&g_cycle_next[dev], 1u, __ATOMIC_RELAXED) % GH_CYCLE_SLOTS;
+		a.ws = g_cycle_pool[dev] + (size_t)GH_POOL_WS_WORDS * slot;
+	}
+	return launch_cycle_multi(g, table_d, a, tiles, compact, stats_d, s);
 }
 
 extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
@@ -428,39 +585,8 @@ extern "C" int gpuhash_cycle_ex(const gpuhash_geom_t *g, void *table_d,
 		const void *const *blk_input_d, const int *blk_elem_num_d, int num_blks,
 		gpuhash_stats_t *stats_d, void *stream)
 {
-	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || !table_d) return -1;
-	if ((n_search && (!selem_d || !out_d)) || (n_delete && !delem_d) || (n_insert && !ielem_d)) return -1;
-	if (blk_input_d && (!blk_elem_num_d || num_blks < 1 || n_insert)) return -1;
-	int dev = 0;
-	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-	if (!g_cycle_counters[dev]) {                    /* first use on this device (not allowed while a stream is capturing: */
-		int rc = gpuhash_init_device();              /*  gpuhash_index_create and the bench loops call this up front)      */
-		if (rc) return rc;
-	}
-	gh::CycleArgs a;
-	a.search_in = (const uint2 *)selem_d; a.search_out = (uint2 *)out_d; a.n_search = n_search;
-	a.delete_in = (const uint32_t *)delem_d; a.n_delete = n_delete;
-	a.insert_in = (const uint32_t *)ielem_d; a.n_insert = n_insert;
-	a.blk_input = (const uint32_t *const *)blk_input_d; a.blk_elem_num = blk_elem_num_d; a.num_blks = num_blks;
-	const size_t sms = (size_t)sm_count_now();
-	const size_t upl = g->layout == GPUHASH_LAYOUT_PAIRS ? 2 : 1;               /* lanes per update request */
-	size_t sc = ((n_search + gh::kTileReq - 1) / gh::kTileReq + 7) / 8;          /* 8 warps per CTA, one 64-request tile per warp and round */
-	size_t dc = (n_delete * upl + 255) / 256, ic = (n_insert * upl + 255) / 256;
-	if (sc > sms * 8) sc = sms * 8;
-	if (dc > sms * 8) dc = sms * 8;
-	if (ic > sms * 8) ic = sms * 8;
-	if (blk_input_d) ic = sms * (size_t)(g_tune.insert_ctas_per_sm > 0 ? g_tune.insert_ctas_per_sm : 4);
-	a.search_ctas = (unsigned)sc; a.delete_ctas = (unsigned)dc; a.insert_ctas = (unsigned)ic;
-	const unsigned total = a.search_ctas + a.delete_ctas + a.insert_ctas;
-	if (total == 0) return 0;
-	/* a counter slot is reused GH_CYCLE_SLOTS launches later; the launch that used it has cleared it long before */
-	a.counters = g_cycle_counters[dev] + 4 * (g_cycle_next[dev]++ % GH_CYCLE_SLOTS);
-	gh::Geom gg = to_geom(g);
-	if (gg.layout == gh::kLayoutPairs)
-		gh::cycle_kernel<true><<<total, 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, (gh::Stats *)stats_d, a);
-	else
-		gh::cycle_kernel<false><<<total, 256, 0, (cudaStream_t)stream>>>((gh::Bucket *)table_d, gg, (gh::Stats *)stats_d, a);
-	return (int)cudaGetLastError();
+	return gpuhash_cycle_ws_ex(g, table_d, selem_d, n_search, out_d, delem_d, n_delete, ielem_d, n_insert,
+			blk_input_d, blk_elem_num_d, num_blks, 0, NULL, stats_d, stream);
 }
 
 /* ------------------------------------------------------------------ legacy C ABI */

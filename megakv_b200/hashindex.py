@@ -207,6 +207,29 @@ class GpuHashIndex:
         N.check(self.L.gpuhash_index_sync(self.h), "gpuhash_index_sync")
         self._keep.clear()
 
+    def submit_all(self, batches):
+        """One scheduler cycle of ALL workers in ONE launch (mega_scheduler.c:393-504): batches[w] = dict with optional
+        'search', 'delete', 'insert' arrays of worker w.  Returns (ticket, [result array per worker]); results are valid
+        after wait(ticket) or sync()."""
+        descs = (N.Batch * len(batches))()
+        outs = []
+        for w, b in enumerate(batches):
+            s = np.ascontiguousarray(b.get("search"), dtype=SEL_DT) if b.get("search") is not None else np.empty(0, SEL_DT)
+            d = np.ascontiguousarray(b.get("delete"), dtype=IEL_DT) if b.get("delete") is not None else np.empty(0, IEL_DT)
+            i = np.ascontiguousarray(b.get("insert"), dtype=IEL_DT) if b.get("insert") is not None else np.empty(0, IEL_DT)
+            out = np.zeros(2 * len(s), dtype=np.uint32)
+            self._keep.append((s, d, i, out))
+            descs[w] = N.Batch(s.ctypes.data if len(s) else None, out.ctypes.data if len(s) else None,
+                               d.ctypes.data if len(d) else None, i.ctypes.data if len(i) else None, len(s), len(d), len(i), 0)
+            outs.append(out)
+        ticket = self.L.gpuhash_index_submit_all(self.h, descs, len(batches))
+        if ticket < 0:
+            raise N.GpuHashError(f"gpuhash_index_submit_all failed: {ticket}")
+        return ticket, outs
+
+    def wait(self, ticket):
+        N.check(self.L.gpuhash_index_wait(self.h, ticket), "gpuhash_index_wait")
+
     def cycle(self, search=None, delete=None, insert=None, worker=0):
         out = self.submit(worker, search, delete, insert)
         self.sync()
