@@ -127,6 +127,9 @@ typedef struct gpuhash_batch_s {
 size_t gpuhash_cycle_workspace_bytes(int max_batches);
 /* 1 if a phase wait of a cycle kernel on the current device timed out since the last reset (read after synchronising) */
 int gpuhash_cycle_error(int reset);
+/* cap on the cycle kernel's persistent grid, CTAs (of 8 warps) per SM; 0 = fill the GPU (default).  Host-link-bound cycles
+ * (zero-copy batches) are served by a fraction of the warps; a small grid lets consecutive cycles be resident together. */
+void gpuhash_set_cycle_ctas_per_sm(int n);
 int gpuhash_cycle_multi_ex(const gpuhash_geom_t *g, void *table_d, const gpuhash_batch_t *batches_h,
 		const gpuhash_batch_t *batches_d, int num_batches, int compact, void *workspace_d,
 		gpuhash_stats_t *stats_d, void *stream);

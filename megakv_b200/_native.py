@@ -80,6 +80,7 @@ SYMBOLS = {
     "gpuhash_cycle_multi_ex": (_i, [_gp, _vp, C.POINTER(Batch), _vp, _i, _i, _vp, _vp, _vp]),
     "gpuhash_cycle_workspace_bytes": (_sz, [_i]),
     "gpuhash_cycle_error": (_i, [_i]),
+    "gpuhash_set_cycle_ctas_per_sm": (None, [_i]),
     "gpuhash_device_count": (_i, []),
     "gpuhash_set_device": (_i, [_i]),
     "gpuhash_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),

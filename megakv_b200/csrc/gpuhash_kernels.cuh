@@ -63,6 +63,17 @@ struct Stats {                            // == gpuhash_stats_t (gpuhash_ex.h)
 
 /* ------------------------------------------------------------------ memory ops */
 
+// How much of a missing 128 B line L2 fetches from HBM.  Measured on B200 (tools/gather_flavours, ncu dram__sectors_read per
+// random 32 B access, profiles/r02_l2_requests.md): 3.98 sectors with a plain load of any flavour, cache policy or
+// cudaLimitMaxL2FetchGranularity -- and 2.00 with the .L2::64B qualifier (SASS LTC64B).  A bucket is 64 B, 64 B aligned: with
+// the qualifier a probe moves exactly its bucket and nothing else, halving the DRAM bytes of every table access.  (The RATE of
+// random probes does not change: ~47 G/s is a request limit, not a byte limit.)  -DGH_LTC_PLAIN restores plain loads for A/B runs.
+#ifdef GH_LTC_PLAIN
+#define GH_LTC ""
+#else
+#define GH_LTC ".L2::64B"
+#endif
+
 // Table rows during search.  Random rows have no reuse inside a launch, so they are not
 // allocated in L1.  Deliberately NOT .nc: kernels of other streams may be inserting into the
 // same table (mega_scheduler.c runs one stream per worker with no cross-stream order), and a
@@ -70,7 +81,7 @@ struct Stats {                            // == gpuhash_stats_t (gpuhash_ex.h)
 __device__ __forceinline__ Row ld_row_ro(const uint32_t* p)
 {
 	Row r;
-	asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	asm volatile("ld.global.L1::no_allocate" GH_LTC ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
 		  "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
 	return r;
@@ -81,7 +92,7 @@ __device__ __forceinline__ Row ld_row_ro(const uint32_t* p)
 __device__ __forceinline__ Row ld_row_strong(const uint32_t* p)
 {
 	Row r;
-	asm volatile("ld.relaxed.gpu.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	asm volatile("ld.relaxed.gpu.global" GH_LTC ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]),
 		  "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p) : "memory");
 	return r;
@@ -90,7 +101,7 @@ __device__ __forceinline__ Row ld_row_strong(const uint32_t* p)
 __device__ __forceinline__ uint32_t ld_u32_ro(const uint32_t* p)
 {
 	uint32_t v;
-	asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	asm volatile("ld.global.L1::no_allocate" GH_LTC ".u32 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
 }
 
@@ -1166,10 +1177,14 @@ fold_keys_kernel(const unsigned char* __restrict__ keys, size_t stride, uint32_t
 // they are held by running warps or finished.  No assumption about the order in which CTAs are dispatched, about how
 // many are resident, or about other kernels sharing the GPU (the first version ordered the phases by blockIdx).
 // Per worker the order is the reference's in-stream order search -> delete -> insert; workers are unordered against
-// each other, like the reference's streams.  Waits are bounded (timeout -> error word, the warp goes on).
-//   workspace `ws` (caller-owned, zero before the first launch, left zero by every launch):
-//     [0] tile ticket  [1] CTAs finished  [2] error (sticky, never cleared by the kernel)  [3] -
-//     [4 + 2w] search tiles of worker w finished   [5 + 2w] delete tiles of worker w finished
+// each other, like the reference's streams: a delete tile of worker w waits for w's search tiles only, an insert tile
+// for w's search and delete tiles.  In phase-major ticket order those were handed out long before, so the waits are
+// short or empty and no SM slot idles through a cycle-wide drain.  A warp publishes finished tiles (fence + one add
+// on the worker's counter) when it leaves a claim or a span.  Waits are bounded (timeout -> error word, warp goes on).
+//   workspace `ws` (caller-owned, zero before the first launch, left zero by every launch), 32-bit words:
+//     [0] tile ticket  [1] CTAs finished  [2] error (sticky, never cleared by the kernel)
+//     [32 + 16 w] search tiles of worker w finished   [40 + 16 w] delete tiles of worker w finished
+//   (the ticket, hammered by every warp, and each polled counter sit in different 32 B sectors)
 struct BatchDesc {                                        // == gpuhash_batch_t (gpuhash_ex.h)
 	const void* search_in; void* search_out;              // selem_t[n_search]; loc_t[2 n_search] (compact: loc_t[n_search])
 	const void* delete_in; const void* insert_in;         // delem_t[n_delete]; ielem_t[n_insert]
@@ -1187,16 +1202,18 @@ struct MultiArgs {
 	const uint32_t* const* seg_ptrs; const int* seg_counts; int num_segs;   // extra insert spans of worker 0 (gpu_hash_insert's
 	                                                                        // blk_input / blk_elem_num: both live in device memory)
 	uint32_t* ws;
+	uint32_t upd_tile;                                    // requests per delete / insert tile: 16, 32 or 64 (small cycles take small
+	                                                      // tiles so that a lone batch's updates spread over many warps)
 	volatile uint32_t* err_host;                          // optional pinned word the host polls after its sync
 	unsigned long long timeout_ns;
 };
 
 struct SpanTable {                                        // views into dynamic shared memory, built by every CTA
-	const void** in;                                      // [spans]
-	void** out;                                           // [W]
-	uint32_t* n;                                          // [spans]
-	uint32_t* first;                                      // [spans + 1]: first tile of span s; first[spans] = all tiles
-	int spans, W;
+	unsigned char* base; int spans, W;                    // (derived from kernel parameters: nothing here needs a register for long)
+	__device__ __forceinline__ const void*& in(int s) const { return ((const void**)base)[s]; }                      // [spans]
+	__device__ __forceinline__ void*& out(int w) const { return ((void**)(base + (size_t)spans * 8))[w]; }           // [W]
+	__device__ __forceinline__ uint32_t& n(int s) const { return ((uint32_t*)(base + (size_t)spans * 8 + (size_t)W * 8))[s]; }                    // [spans]
+	__device__ __forceinline__ uint32_t& first(int s) const { return ((uint32_t*)(base + (size_t)spans * 8 + (size_t)W * 8 + (size_t)spans * 4))[s]; }   // [spans + 1]
 };
 __host__ __device__ inline size_t span_table_bytes(int W, int segs)
 {
@@ -1216,27 +1233,29 @@ __device__ __forceinline__ void span_table_build(SpanTable& S, unsigned char* sm
 {
 	const int W = a.W, segs = a.num_segs;
 	const int spans = 3 * W + segs;
-	S.in = (const void**)smem; S.out = (void**)(smem + (size_t)spans * 8);
-	S.n = (uint32_t*)(smem + (size_t)spans * 8 + (size_t)W * 8); S.first = S.n + spans;
-	S.spans = spans; S.W = W;
+	S.base = smem; S.spans = spans; S.W = W;
 	for (int w = threadIdx.x; w < W; w += blockDim.x) {
 		const BatchDesc d = a.descs ? a.descs[w] : a.d0;
-		S.in[w] = d.search_in; S.out[w] = d.search_out; S.n[w] = d.n_search;
-		S.in[W + w] = d.delete_in; S.n[W + w] = d.n_delete;
-		S.in[2 * W + w] = d.insert_in; S.n[2 * W + w] = d.n_insert;
+		S.in(w) = d.search_in; S.out(w) = d.search_out; S.n(w) = d.n_search;
+		S.in(W + w) = d.delete_in; S.n(W + w) = d.n_delete;
+		S.in(2 * W + w) = d.insert_in; S.n(2 * W + w) = d.n_insert;
 	}
 	for (int k = threadIdx.x; k < segs; k += blockDim.x) {
 		const int c = a.seg_counts[k];
-		S.in[3 * W + k] = a.seg_ptrs[k]; S.n[3 * W + k] = c > 0 ? (uint32_t)c : 0u;
+		S.in(3 * W + k) = a.seg_ptrs[k]; S.n(3 * W + k) = c > 0 ? (uint32_t)c : 0u;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t acc = 0;
-		for (int s = 0; s < spans; s++) {
-			S.first[s] = acc;
-			acc += s < W ? tiles_of_search(S.in[s], S.n[s]) : (S.n[s] + kTileReq - 1) / kTileReq;
-		}
-		S.first[spans] = acc;
+	if (threadIdx.x < 32) {                               // exclusive prefix of the tile counts by one warp
+		const int per = (spans + 31) / 32, lo = (int)threadIdx.x * per, hi = min(spans, lo + per);
+		uint32_t sum = 0;
+		const uint32_t ut = a.upd_tile;
+		for (int s = lo; s < hi; s++) sum += s < W ? tiles_of_search(S.in(s), S.n(s)) : (S.n(s) + ut - 1) / ut;
+		uint32_t inc = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+		uint32_t acc = inc - sum;
+		for (int s = lo; s < hi; s++) { S.first(s) = acc; acc += s < W ? tiles_of_search(S.in(s), S.n(s)) : (S.n(s) + ut - 1) / ut; }
+		if (threadIdx.x == 31) S.first(spans) = inc;
 	}
 	__syncthreads();
 }
@@ -1244,7 +1263,7 @@ __device__ __forceinline__ void span_table_build(SpanTable& S, unsigned char* sm
 __device__ __forceinline__ int span_of_tile(const SpanTable& S, uint32_t t)          // largest s with first[s] <= t (t < all tiles)
 {
 	int lo = 0, hi = S.spans;                             // invariant: first[lo] <= t < first[hi]
-	while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.first[mid] <= t) lo = mid; else hi = mid; }
+	while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.first(mid) <= t) lo = mid; else hi = mid; }
 	return lo;
 }
 
@@ -1259,9 +1278,11 @@ __device__ __forceinline__ void tiles_wait(const uint32_t* c, uint32_t target, c
 	if (target == 0) return;
 	if (lane == 0 && ld_acquire_gpu_u32(c) < target) {
 		unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+		unsigned ns = 128u;
 		for (;;) {
-			__nanosleep(128);
+			__nanosleep(ns);
 			if (ld_acquire_gpu_u32(c) >= target) break;
+			if (ns < 2048u) ns <<= 1;                      // back off: thousands of warps may be polling this one word
 			unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
 			if (t1 - t0 > a.timeout_ns) {                // never seen in practice; a hung box is worse than a flagged batch
 				atomicExch(a.ws + 2, 1u);
@@ -1273,9 +1294,24 @@ __device__ __forceinline__ void tiles_wait(const uint32_t* c, uint32_t target, c
 	__syncwarp();
 }
 
+// publish `count` finished tiles on counter ws[slot]: everything this warp read or wrote for them happens-before the add
+__device__ __forceinline__ void tiles_publish(uint32_t* ws, uint32_t slot, uint32_t& count, unsigned lane)
+{
+	if (count == 0) return;                               // warp-uniform
+	__syncwarp();
+	if (lane == 0) { __threadfence(); atomicAdd(ws + slot, count); }
+	count = 0;
+}
+constexpr uint32_t kWsCounters = 32, kWsPerWorker = 16, kWsDelete = 8;     // word offsets inside the workspace
+__host__ __device__ inline size_t cycle_workspace_words(int max_batches) { return kWsCounters + (size_t)kWsPerWorker * (size_t)max_batches; }
+
 #ifndef GH_CYCLE_MIN_CTAS
-#define GH_CYCLE_MIN_CTAS 3          /* 80 registers, no spills; 4 forces 64 registers and spills 40-56 B per thread */
+#define GH_CYCLE_MIN_CTAS 2          /* measured, 64 batches of 64 K per launch, mixed / search only, Gops/s: 2 CTAs per SM (128
+                                        registers) 19.5 / 19.7, 3 (80 registers, 24-48 B spilled) 17.7 / 17.5, 4 (64) 16.4 / 16.5:
+                                        16 warps with four 32 B loads per lane in flight cover the ~47 G probes/s the memory takes */
 #endif
+constexpr uint32_t kMaxClaim = 4;                         // tiles per ticket at most
+
 template <bool kPairs, bool kCompact>
 __global__ void __launch_bounds__(256, GH_CYCLE_MIN_CTAS)
 cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
@@ -1286,36 +1322,53 @@ cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
 	pdl_enter();
 	span_table_build(S, span_smem, a);
 	const unsigned lane = threadIdx.x & 31u;
-	const uint32_t total = S.first[S.spans];
+	const uint32_t total = S.first(S.spans);
 	const int W = S.W;
+	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
 	uint32_t h1 = 0, h2 = 0;
+	uint32_t pend = 0, pend_slot = 0;                     // tiles this warp finished and has not published yet, and their counter
 
-	// Tickets are taken two tiles ahead of their use: the atomic issued at the top of an iteration is only read
-	// (shuffled out of lane 0) at its bottom, and the requests of the NEXT tile are already in flight while this
-	// one is probed -- neither latency is on the warp's critical path.
-	auto claim_issue = [&]() -> uint32_t { return lane == 0 ? atomicAdd(a.ws + 0, 1u) : 0u; };
+	// Tickets.  A claim takes 1..kMaxClaim consecutive tiles -- many while there is plenty left, one near the end
+	// (guided self-scheduling: balance at the tail, few same-address atomics before it).  Claims are issued one chunk
+	// ahead of their use and only read (shuffled out of lane 0) when the current chunk runs out; the requests of the
+	// NEXT tile are in flight while this one is probed.  Neither latency is on the warp's critical path.
+	auto claim_size = [&](uint32_t seen) -> uint32_t {
+		const uint32_t rem = total > seen ? total - seen : 0u;
+		return min(kMaxClaim, max(1u, rem / (6u * nwarps)));
+	};
+	auto claim_issue = [&](uint32_t k) -> uint32_t { return lane == 0 ? atomicAdd(a.ws + 0, k) : 0u; };
 	// requests of a search tile (this lane's 16 B); nothing for other tiles
 	auto prefetch = [&](uint32_t t, int s) -> uint4 {
 		if (t >= total || s >= W) return make_uint4(0u, 0u, 0u, 0u);
-		const uint2* in = (const uint2*)S.in[s];
+		const uint2* in = (const uint2*)S.in(s);
 		const uint32_t head = ((uintptr_t)in & 15u) ? 1u : 0u;
-		const uint32_t n_a = S.n[s] - head, r0 = (t - S.first[s]) * kTileReq;
+		const uint32_t n_a = S.n(s) - head, r0 = (t - S.first(s)) * kTileReq;
 		return warp_tile_load<false>(in + head + r0, min((uint32_t)kTileReq, n_a - min(n_a, r0)), lane);
 	};
 
-	uint32_t cur = __shfl_sync(0xffffffffu, claim_issue(), 0);
-	uint32_t nxt = __shfl_sync(0xffffffffu, claim_issue(), 0);
-	int s_cur = cur < total ? span_of_tile(S, cur) : 0;
-	uint4 v = prefetch(cur, s_cur);
-	while (cur < total) {
-		const uint32_t raw_nn = claim_issue();
-		const int s_nxt = nxt < total ? span_of_tile(S, nxt) : 0;
-		const uint4 vn = prefetch(nxt, s_nxt);            // in flight while this tile is probed
+	uint32_t k_cur = claim_size(0), k_nxt = k_cur;
+	const uint32_t raw_a = claim_issue(k_cur), raw_b = claim_issue(k_nxt);           // two atomics in flight together
+	uint32_t c0 = __shfl_sync(0xffffffffu, raw_a, 0), c1 = c0 + k_cur;
+	uint32_t n0 = __shfl_sync(0xffffffffu, raw_b, 0), n1 = n0 + k_nxt;
+	uint32_t seen = n1, raw_nn = 0, k_nn = 1;
+	uint32_t t = c0;
+	int s_cur = t < total ? span_of_tile(S, t) : 0;
+	uint4 v = prefetch(t, s_cur);
+	while (t < total) {
+		if (t == c0) { k_nn = claim_size(seen); raw_nn = claim_issue(k_nn); }        // the chunk after next
+		const bool last_of_chunk = t + 1 >= c1;
+		const uint32_t tn = last_of_chunk ? n0 : t + 1;
+		int s_nxt = s_cur;
+		if (tn < total) {
+			if (last_of_chunk) s_nxt = span_of_tile(S, tn);
+			else while (tn >= S.first(s_nxt + 1)) s_nxt++;
+		}
+		const uint4 vn = prefetch(tn, s_nxt);             // in flight while this tile is probed
 		const int s = s_cur;
-		const uint32_t lt = cur - S.first[s];             // tile inside its span
+		const uint32_t lt = t - S.first(s);               // tile inside its span
 		if (s < W) {                                      // ---- search
-			const uint2* in = (const uint2*)S.in[s]; char* out = (char*)S.out[s];
-			const uint32_t n = S.n[s];
+			const uint2* in = (const uint2*)S.in(s); char* out = (char*)S.out(s);
+			const uint32_t n = S.n(s);
 			const uint32_t head = ((uintptr_t)in & 15u) ? 1u : 0u;
 			const bool out_vec = (((uintptr_t)out + kOutBytes * head) & (kCompact ? 7u : 15u)) == 0;
 			if (head && lt == 0) {                        // the request in front of the first aligned tile
@@ -1326,18 +1379,20 @@ cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
 			const uint32_t valid = min((uint32_t)kTileReq, n_a - min(n_a, r0));
 			if (valid)
 				warp_tile_search<kPairs, false, kCompact>(table, g, in + head + r0, out + kOutBytes * (head + (size_t)r0), valid, out_vec, v, lane, h1, h2);
-			__syncwarp();
-			if (lane == 0) { __threadfence(); atomicAdd(a.ws + 4 + 2 * s, 1u); }
-		} else {                                          // ---- delete / insert
+			const uint32_t slot = kWsCounters + kWsPerWorker * (uint32_t)s;
+			if (slot != pend_slot) { tiles_publish(a.ws, pend_slot, pend, lane); pend_slot = slot; }
+			pend++;
+		} else {                                          // ---- delete / insert: after the searches (and deletes) of ITS worker
 			const bool is_delete = s < 2 * W;
 			const int w = is_delete ? s - W : (s < 3 * W ? s - 2 * W : 0);       // segments belong to worker 0
-			tiles_wait(a.ws + 4 + 2 * w, S.first[w + 1] - S.first[w], a, lane);
-			if (!is_delete) tiles_wait(a.ws + 5 + 2 * w, S.first[W + w + 1] - S.first[W + w], a, lane);
-			const uint32_t* in = (const uint32_t*)S.in[s];
-			const uint32_t n = S.n[s], r0 = lt * kTileReq;
+			tiles_publish(a.ws, pend_slot, pend, lane);   // this warp's own finished tiles first: nobody waits on a waiter
+			tiles_wait(a.ws + kWsCounters + kWsPerWorker * w, S.first(w + 1) - S.first(w), a, lane);
+			if (!is_delete) tiles_wait(a.ws + kWsCounters + kWsPerWorker * w + kWsDelete, S.first(W + w + 1) - S.first(W + w), a, lane);
+			const uint32_t* in = (const uint32_t*)S.in(s);
+			const uint32_t n = S.n(s), r0 = lt * a.upd_tile;
 			if (kPairs) {                                 // two lanes per request: 16 requests per round
 #pragma unroll 1
-				for (uint32_t r = 0; r < (uint32_t)kTileReq; r += 16) {
+				for (uint32_t r = 0; r < a.upd_tile; r += 16) {
 					if (r0 + r >= n) break;               // warp-uniform
 					const uint32_t i = r0 + r + (lane >> 1);
 					const bool have = i < n;
@@ -1352,9 +1407,9 @@ cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
 				}
 			} else {
 #pragma unroll 1
-				for (uint32_t r = 0; r < (uint32_t)kTileReq; r += 32) {
+				for (uint32_t r = 0; r < a.upd_tile; r += 32) {
 					const uint32_t i = r0 + r + lane;
-					if (i < n) {
+					if (i < n && r + lane < a.upd_tile) {
 						const uint32_t x = ld_stream_u32(in + 3 * (size_t)i), y = ld_stream_u32(in + 3 * (size_t)i + 1), z = ld_stream_u32(in + 3 * (size_t)i + 2);
 						if (is_delete) {
 							const int zc = delete_one<false>(table, g, x, y, z);
@@ -1365,12 +1420,17 @@ cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
 					}
 				}
 			}
-			__syncwarp();
-			if (is_delete && lane == 0) { __threadfence(); atomicAdd(a.ws + 5 + 2 * w, 1u); }
+			if (is_delete) { pend_slot = kWsCounters + kWsPerWorker * (uint32_t)w + kWsDelete; pend = 1; }
 		}
-		cur = nxt; s_cur = s_nxt; v = vn;
-		nxt = __shfl_sync(0xffffffffu, raw_nn, 0);
+		if (last_of_chunk) {
+			tiles_publish(a.ws, pend_slot, pend, lane);   // bounded delay: others may be waiting for exactly these tiles
+			c0 = n0; c1 = n1;
+			n0 = __shfl_sync(0xffffffffu, raw_nn, 0); n1 = n0 + k_nn;
+			seen = max(seen, n1);
+		}
+		t = tn; s_cur = s_nxt; v = vn;
 	}
+	tiles_publish(a.ws, pend_slot, pend, lane);
 	if (st) {                                             // every quad's first lane counted its own hits
 		if (h1) atomicAdd(&st->search_hits_b1, (unsigned long long)h1);
 		if (h2) atomicAdd(&st->search_hits_b2, (unsigned long long)h2);
@@ -1381,7 +1441,7 @@ cycle_multi_kernel(Bucket* table, Geom g, Stats* st, MultiArgs a)
 		__threadfence();
 		if (atomicAdd(a.ws + 1, 1u) == gridDim.x - 1) {
 			a.ws[0] = 0; a.ws[1] = 0;
-			for (int w = 0; w < W; w++) { a.ws[4 + 2 * w] = 0; a.ws[5 + 2 * w] = 0; }
+			for (int w = 0; w < W; w++) { a.ws[kWsCounters + kWsPerWorker * w] = 0; a.ws[kWsCounters + kWsPerWorker * w + kWsDelete] = 0; }
 			__threadfence();
 		}
 	}

@@ -405,7 +405,7 @@ extern "C" int gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, uns
  * stream and one per submit_all slot).  The stateless entry points (gpuhash_cycle_ex, the legacy gpu_delete_insert) take a
  * slot from a per-device pool by an atomic round-robin counter: a slot is reused GH_CYCLE_SLOTS launches later. */
 #define GH_CYCLE_SLOTS 4096
-#define GH_POOL_WS_WORDS 8                        /* ticket, finished, error, -, and one worker's two phase counters */
+#define GH_POOL_WS_WORDS 64                       /* gh::cycle_workspace_words(1) = 48, rounded to 256 B */
 static unsigned int *g_cycle_pool[64];            /* per device: GH_CYCLE_SLOTS x GH_POOL_WS_WORDS words, zero */
 static unsigned int g_cycle_next[64];
 static volatile unsigned int *g_cycle_err[64];    /* per device: pinned word a cycle kernel sets when a phase wait timed out */
@@ -448,7 +448,7 @@ extern "C" int gpuhash_cycle_error(int reset)
 extern "C" size_t gpuhash_cycle_workspace_bytes(int max_batches)
 {
 	if (max_batches < 1) max_batches = 1;
-	return (((size_t)4 + 2 * (size_t)max_batches) * sizeof(unsigned int) + 63) & ~(size_t)63;
+	return ((gh::cycle_workspace_words(max_batches) * sizeof(unsigned int)) + 127) & ~(size_t)127;
 }
 
 static unsigned long long cycle_timeout_ns(void)
@@ -460,18 +460,36 @@ static unsigned long long cycle_timeout_ns(void)
 
 /* shape + launch shared by every entry point of the one-launch cycle.  total_tiles: from host-side counts (0 = unknown:
  * full persistent grid) */
+/* resident CTAs per SM of a cycle kernel variant (the tickets do not need a resident grid to be correct -- it is simply the
+ * smallest grid that fills the GPU: fewer span tables to build, fewer ticket atomics at the start) */
+template <typename K>
+static int cycle_ctas_per_sm(K kernel, int threads, size_t smem, int *cache)
+{
+	if (*cache <= 0) {
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 2048 / threads / 2; }
+		*cache = n;
+	}
+	return *cache;
+}
+
+/* GPUHASH_CYCLE_CTAS_PER_SM / gpuhash_set_cycle_ctas_per_sm: cap on the persistent grid of the cycle kernel (0 = fill the GPU).
+ * A cycle whose batches live in pinned HOST memory is bound by the host link, which a fraction of the warps saturates; with
+ * one CTA per SM two consecutive cycles are resident together and the link never idles at a cycle boundary. */
+static int g_cycle_ctas_cap = -1;
+extern "C" void gpuhash_set_cycle_ctas_per_sm(int n) { g_cycle_ctas_cap = n > 0 ? n : 0; }
+
 static int launch_cycle_multi(const gpuhash_geom_t *g, void *table_d, gh::MultiArgs &a, size_t total_tiles, int compact,
 		gpuhash_stats_t *stats_d, cudaStream_t s)
 {
+	if (g_cycle_ctas_cap < 0) { const char *e = getenv("GPUHASH_CYCLE_CTAS_PER_SM"); g_cycle_ctas_cap = e && *e ? atoi(e) : 0; if (g_cycle_ctas_cap < 0) g_cycle_ctas_cap = 0; }
 	const size_t sms = (size_t)sm_count_now();
 	/* small cycles (a lone 64 K batch is ~1000 tiles) take 2-warp CTAs so that they still reach every SM */
 	const unsigned threads = total_tiles && total_tiles <= sms * 16 ? 64u : 256u;
 	const size_t wpc = threads / 32;
-	size_t blocks = sms * (2048 / threads);
-	if (total_tiles) { const size_t need = (total_tiles + wpc - 1) / wpc; if (need < blocks) blocks = need; }
-	if (blocks == 0) blocks = 1;
 	const size_t smem = gh::span_table_bytes(a.W, a.num_segs);
 	a.timeout_ns = cycle_timeout_ns();
+	a.upd_tile = threads == 64u ? 16u : 64u;
 	{
 		int dev = 0;
 		if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
@@ -481,11 +499,26 @@ static int launch_cycle_multi(const gpuhash_geom_t *g, void *table_d, gh::MultiA
 	}
 	gh::Geom gg = to_geom(g);
 	gh::Bucket *t = (gh::Bucket *)table_d; gh::Stats *st = (gh::Stats *)stats_d;
-	const bool pairs = gg.layout == gh::kLayoutPairs;
-	if (pairs && !compact)      gh::cycle_multi_kernel<true, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
-	else if (pairs)             gh::cycle_multi_kernel<true, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
-	else if (!compact)          gh::cycle_multi_kernel<false, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
-	else                        gh::cycle_multi_kernel<false, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a);
+	const int variant = (gg.layout == gh::kLayoutPairs ? 0 : 2) + (compact ? 1 : 0);
+	static int occ[4][2];                              /* [variant][threads == 256] */
+	int *oc = &occ[variant][threads == 256];
+	int per_sm;
+	switch (variant) {
+	case 0:  per_sm = cycle_ctas_per_sm(gh::cycle_multi_kernel<true, false>, (int)threads, smem, oc); break;
+	case 1:  per_sm = cycle_ctas_per_sm(gh::cycle_multi_kernel<true, true>, (int)threads, smem, oc); break;
+	case 2:  per_sm = cycle_ctas_per_sm(gh::cycle_multi_kernel<false, false>, (int)threads, smem, oc); break;
+	default: per_sm = cycle_ctas_per_sm(gh::cycle_multi_kernel<false, true>, (int)threads, smem, oc); break;
+	}
+	if (g_cycle_ctas_cap > 0 && threads == 256u && per_sm > g_cycle_ctas_cap) per_sm = g_cycle_ctas_cap;
+	size_t blocks = sms * (size_t)per_sm;
+	if (total_tiles) { const size_t need = (total_tiles + wpc - 1) / wpc; if (need < blocks) blocks = need; }
+	if (blocks == 0) blocks = 1;
+	switch (variant) {
+	case 0:  gh::cycle_multi_kernel<true, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a); break;
+	case 1:  gh::cycle_multi_kernel<true, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a); break;
+	case 2:  gh::cycle_multi_kernel<false, false><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a); break;
+	default: gh::cycle_multi_kernel<false, true><<<(unsigned)blocks, threads, smem, s>>>(t, gg, st, a); break;
+	}
 	return (int)cudaGetLastError();
 }
 

@@ -76,6 +76,24 @@ void orc_search(const void *table, const orc_geom_t *g,
 		search_one(t, g, in[i].sig, in[i].hash, &out[2 * i]);
 }
 
+/* The same loop with the two buckets of request i + 12 prefetched while request i is compared: what any CPU
+ * implementation that cares about throughput does (the table is far bigger than the caches, every probe is a DRAM
+ * miss).  Results are orc_search's word for word (tests/test_oracle.py); used by the thread pool of the CPU baseline so
+ * that the GPU is not compared with a latency-bound loop. */
+void orc_search_pf(const void *table, const orc_geom_t *g,
+		const orc_sel_t *in, size_t n, uint32_t *out)
+{
+	const bucket_t *t = (const bucket_t *)table;
+	const size_t ahead = 12;
+	for (size_t i = 0; i < n; i++) {
+		if (i + ahead < n) {
+			__builtin_prefetch(&t[orc_bucket1(g, in[i + ahead].hash)], 0, 0);
+			__builtin_prefetch(&t[orc_bucket2(g, in[i + ahead].hash, in[i + ahead].sig)], 0, 0);
+		}
+		search_one(t, g, in[i].sig, in[i].hash, &out[2 * i]);
+	}
+}
+
 /* ------------------------------------------------------------------ insert */
 
 /* lowest lane whose signature equals sig: __ffs(ballot)-1 at gpu_hash.cu:120,282,344 */
@@ -331,4 +349,142 @@ void orc_insert_mt(void *table, const orc_geom_t *g, const orc_iel_t *in, size_t
 		pthread_create(&th[k], NULL, insert_worker, &jobs[k]);
 	}
 	for (int k = 0; k < threads; k++) pthread_join(th[k], NULL);
+}
+
+/* ---------------------------------------------- persistent pool (CPU baseline) */
+
+/* The CPU arm of bench.py: one scheduler cycle of `batches` worker batches on the host's cores, with threads that live
+ * across cycles (one per core, handed work through a barrier) instead of a pthread_create per batch.
+ *   phase 1  every thread zeroes its slice of `out` (the caller's memset, mega_scheduler.c:406) and searches its slice
+ *            of ALL batches' requests (gpu_hash.cu:28-75) -- the table is read-only in this phase
+ *   phase 2  inserts (gpu_hash.cu:231-433 / :77-229): the 8 bucket ranges with equal top IBLOCK_P bits are closed under
+ *            the alternate-bucket function (gpu_hash.h:67-69), so range r is owned by thread r % min(threads, 8), which
+ *            walks all batches in order -- the table equals orc_insert() over the concatenated batches
+ * Per batch that is the reference's in-stream order search -> insert; batches are unordered against each other in the
+ * reference (one stream per worker, mega_scheduler.c:276-280), and "all searches, then all inserts" is one such order. */
+struct orc_pool_s {
+	int threads;
+	pthread_t *th;
+	pthread_barrier_t start, done;
+	int stop;
+	/* the job */
+	int kind;                              /* 0 cycle, 1 insert only, 2 preload from the key stream */
+	void *table; const orc_geom_t *g;
+	const orc_sel_t *sel; uint32_t *out; size_t n_search_total;
+	const orc_iel_t *iel; size_t n_insert_total;
+	uint64_t seed, first, count;
+};
+
+typedef struct { struct orc_pool_s *p; int id; } pool_arg_t;
+
+static void pool_insert_range(struct orc_pool_s *p, int id)
+{
+	const orc_geom_t *g = p->g;
+	const int owners = p->threads < 8 ? p->threads : 8;
+	if (id >= owners) return;
+	uint32_t nb = g->hash_mask + 1, shift = 0;
+	if (nb < 8) { if (id == 0) orc_insert(p->table, g, p->iel, p->n_insert_total, NULL); return; }
+	while ((nb >> shift) > 8) shift++;
+	if (p->kind == 2) {                    /* generate the keys here: every owner walks the stream and keeps its ranges */
+		uint64_t state = p->seed + p->first * 0x9E3779B97F4A7C15ULL;
+		for (uint64_t i = 0; i < p->count; i++) {
+			uint64_t key = orc_splitmix64(&state);
+			orc_iel_t e; e.sig = (uint32_t)key; e.hash = (uint32_t)(key >> 32); e.loc = (uint32_t)(p->first + i + 1);
+			if (e.sig == 0) e.sig = 1;
+			if ((int)((orc_bucket1(g, e.hash) >> shift) % (uint32_t)owners) == id) orc_insert(p->table, g, &e, 1, NULL);
+		}
+		return;
+	}
+	for (size_t i = 0; i < p->n_insert_total; i++)
+		if ((int)((orc_bucket1(g, p->iel[i].hash) >> shift) % (uint32_t)owners) == id) orc_insert(p->table, g, &p->iel[i], 1, NULL);
+}
+
+static void *pool_worker(void *a_)
+{
+	pool_arg_t *a = (pool_arg_t *)a_;
+	struct orc_pool_s *p = a->p;
+	const int id = a->id;
+	free(a);
+	for (;;) {
+		pthread_barrier_wait(&p->start);
+		if (p->stop) break;
+		if (p->kind == 0) {
+			size_t lo = p->n_search_total * (size_t)id / (size_t)p->threads, hi = p->n_search_total * (size_t)(id + 1) / (size_t)p->threads;
+			memset(p->out + 2 * lo, 0, (hi - lo) * 2 * sizeof(uint32_t));
+			orc_search_pf(p->table, p->g, p->sel + lo, hi - lo, p->out + 2 * lo);
+			pthread_barrier_wait(&p->done);          /* all searches of the cycle before any insert */
+		}
+		pool_insert_range(p, id);
+		pthread_barrier_wait(&p->done);
+	}
+	return NULL;
+}
+
+orc_pool_t *orc_pool_create(int threads)
+{
+	if (threads < 1) threads = 1;
+	struct orc_pool_s *p = (struct orc_pool_s *)calloc(1, sizeof *p);
+	p->threads = threads;
+	p->th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+	pthread_barrier_init(&p->start, NULL, (unsigned)threads + 1);
+	pthread_barrier_init(&p->done, NULL, (unsigned)threads + 1);
+	for (int k = 0; k < threads; k++) {
+		pool_arg_t *a = (pool_arg_t *)malloc(sizeof *a); a->p = p; a->id = k;
+		pthread_create(&p->th[k], NULL, pool_worker, a);
+	}
+	return p;
+}
+
+int orc_pool_threads(const orc_pool_t *p) { return p->threads; }
+
+void orc_pool_destroy(orc_pool_t *p)
+{
+	p->stop = 1;
+	pthread_barrier_wait(&p->start);
+	for (int k = 0; k < p->threads; k++) pthread_join(p->th[k], NULL);
+	pthread_barrier_destroy(&p->start); pthread_barrier_destroy(&p->done);
+	free(p->th); free(p);
+}
+
+static void pool_run(orc_pool_t *p)
+{
+	pthread_barrier_wait(&p->start);
+	if (p->kind == 0) pthread_barrier_wait(&p->done);
+	pthread_barrier_wait(&p->done);
+}
+
+/* sel / out / iel hold the `batches` batches of the cycle back to back (n_search, 2 n_search, n_insert entries each) */
+void orc_pool_cycle(orc_pool_t *p, void *table, const orc_geom_t *g, const orc_sel_t *sel, size_t n_search, uint32_t *out,
+		const orc_iel_t *iel, size_t n_insert, int batches)
+{
+	p->kind = 0; p->table = table; p->g = g;
+	p->sel = sel; p->out = out; p->n_search_total = n_search * (size_t)batches;
+	p->iel = iel; p->n_insert_total = n_insert * (size_t)batches;
+	pool_run(p);
+}
+
+void orc_pool_insert(orc_pool_t *p, void *table, const orc_geom_t *g, const orc_iel_t *iel, size_t n)
+{
+	p->kind = 1; p->table = table; p->g = g; p->iel = iel; p->n_insert_total = n;
+	pool_run(p);
+}
+
+/* keys first .. first+count-1 of the SURVEY 8(d) stream inserted without materialising them */
+void orc_pool_preload(orc_pool_t *p, void *table, const orc_geom_t *g, uint64_t seed, uint64_t first, uint64_t count)
+{
+	p->kind = 2; p->table = table; p->g = g; p->seed = seed; p->first = first; p->count = count;
+	pool_run(p);
+}
+
+/* n searches for keys drawn uniformly from the first `population` keys of the stream (every one hits once they are in) */
+void orc_gen_queries(uint64_t seed, uint64_t population, size_t n, uint64_t rng_seed, orc_sel_t *out)
+{
+	uint64_t r = rng_seed * 0xD1342543DE82EF95ULL + 0x2545F4914F6CDD1DULL;
+	for (size_t i = 0; i < n; i++) {
+		uint64_t idx = (uint64_t)(((__uint128_t)orc_splitmix64(&r) * population) >> 64);
+		uint64_t state = seed + idx * 0x9E3779B97F4A7C15ULL;
+		uint64_t key = orc_splitmix64(&state);
+		out[i].sig = (uint32_t)key; out[i].hash = (uint32_t)(key >> 32);
+		if (out[i].sig == 0) out[i].sig = 1;
+	}
 }

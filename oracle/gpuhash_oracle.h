@@ -70,6 +70,9 @@ uint32_t orc_bucket2(const orc_geom_t *g, uint32_t hash, uint32_t sig);
 /* out[2n] must be pre-zeroed by the caller: only hits are stored. */
 void     orc_search(const void *table, const orc_geom_t *g,
 		const orc_sel_t *in, size_t n, uint32_t *out);
+/* orc_search with the buckets of a later request prefetched (same results; the CPU baseline's loop) */
+void     orc_search_pf(const void *table, const orc_geom_t *g,
+		const orc_sel_t *in, size_t n, uint32_t *out);
 void     orc_insert(void *table, const orc_geom_t *g,
 		const orc_iel_t *in, size_t n, orc_stats_t *st /* may be NULL, accumulates */);
 void     orc_insert_blocks(void *table, const orc_geom_t *g,
@@ -100,6 +103,20 @@ void     orc_search_mt(const void *table, const orc_geom_t *g,
 void     orc_insert_mt(void *table, const orc_geom_t *g,
 		const orc_iel_t *in, size_t n, int threads);
 double   orc_now_sec(void);
+
+/* Persistent thread pool for the CPU arm of bench.py: threads live across cycles and are handed work through barriers.
+ * orc_pool_cycle = one scheduler cycle of `batches` worker batches (mega_scheduler.c:393-504) on the host: all searches
+ * (index ranges over all threads, `out` zeroed inside like the caller's memset at :406), then all inserts (the 8 closed
+ * bucket ranges over min(threads, 8) threads, batch order kept).  The table ends equal to orc_insert() over the batches. */
+typedef struct orc_pool_s orc_pool_t;
+orc_pool_t *orc_pool_create(int threads);
+int      orc_pool_threads(const orc_pool_t *p);
+void     orc_pool_destroy(orc_pool_t *p);
+void     orc_pool_cycle(orc_pool_t *p, void *table, const orc_geom_t *g, const orc_sel_t *sel, size_t n_search,
+		uint32_t *out, const orc_iel_t *iel, size_t n_insert, int batches);
+void     orc_pool_insert(orc_pool_t *p, void *table, const orc_geom_t *g, const orc_iel_t *iel, size_t n);
+void     orc_pool_preload(orc_pool_t *p, void *table, const orc_geom_t *g, uint64_t seed, uint64_t first, uint64_t count);
+void     orc_gen_queries(uint64_t seed, uint64_t population, size_t n, uint64_t rng_seed, orc_sel_t *out);
 
 #ifdef __cplusplus
 }

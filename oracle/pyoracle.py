@@ -67,6 +67,13 @@ def lib():
         L.orc_search_mt.argtypes = [vp, gp, vp, sz, vp, C.c_int]
         L.orc_insert_mt.argtypes = [vp, gp, vp, sz, C.c_int]
         L.orc_now_sec.restype = C.c_double
+        L.orc_pool_create.argtypes = [C.c_int]; L.orc_pool_create.restype = vp
+        L.orc_pool_threads.argtypes = [vp]; L.orc_pool_threads.restype = C.c_int
+        L.orc_pool_destroy.argtypes = [vp]
+        L.orc_pool_cycle.argtypes = [vp, vp, gp, vp, sz, vp, vp, sz, C.c_int]
+        L.orc_pool_insert.argtypes = [vp, vp, gp, vp, sz]
+        L.orc_pool_preload.argtypes = [vp, vp, gp, u64, u64, u64]
+        L.orc_gen_queries.argtypes = [u64, u64, sz, u64, vp]
         _lib = L
     return _lib
 
@@ -151,6 +158,37 @@ class Oracle:
         """view as [num_buckets, 2, 8]: [:,0,:] signatures, [:,1,:] locations"""
         t = self.table if table is None else np.ascontiguousarray(table).view(np.uint32)
         return t.reshape(-1, 2, 8)
+
+
+class Pool:
+    """persistent host threads for the CPU arm of bench.py (orc_pool_*)"""
+
+    def __init__(self, threads):
+        self.L = lib()
+        self.h = self.L.orc_pool_create(threads)
+        self.threads = self.L.orc_pool_threads(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.orc_pool_destroy(self.h); self.h = None
+
+    def cycle(self, orc, sel, out, iel, batches):
+        """sel [batches * n_search], out uint32 [2 * batches * n_search], iel [batches * n_insert]"""
+        self.L.orc_pool_cycle(self.h, _ptr(orc.table), C.byref(orc.g), _ptr(sel), len(sel) // batches, _ptr(out),
+                              _ptr(iel), len(iel) // batches, batches)
+
+    def insert(self, orc, iel):
+        iel = np.ascontiguousarray(iel, dtype=IEL_DT)
+        self.L.orc_pool_insert(self.h, _ptr(orc.table), C.byref(orc.g), _ptr(iel), len(iel))
+
+    def preload(self, orc, seed, first, count):
+        self.L.orc_pool_preload(self.h, _ptr(orc.table), C.byref(orc.g), seed, first, count)
+
+
+def gen_queries(seed, population, n, rng_seed):
+    sel = np.empty(n, dtype=SEL_DT)
+    lib().orc_gen_queries(seed, population, n, rng_seed, _ptr(sel))
+    return sel
 
 
 def keys(seed, first_index, n):

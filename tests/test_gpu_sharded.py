@@ -70,11 +70,12 @@ def _worker(rank, world, port, exchange, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 @pytest.mark.parametrize("exchange", ["collective", "p2p"])
 def test_sharded_index_on_gpus(gpu, exchange, world):
     """world 1: the whole routed path (scatter, publish, wait, serve, gather) with this GPU as its own peer, so a
-    1-GPU box still runs every kernel of the sharded index; world 2: across NVLink."""
+    1-GPU box still runs every kernel of the sharded index; world 2, 4, 8: one process per GPU across NVLink (skipped on
+    boxes with fewer GPUs; `gpurun --gpus N -- python -m pytest tests/test_gpu_sharded.py -m gpu` runs them)."""
     if gpu.lib().gpuhash_device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp

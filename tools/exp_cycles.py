@@ -44,13 +44,16 @@ def cycles(W, streams, n_insert, reps=3):
     return best
 
 
-for W in (16, 64, 128):
-    for streams in (1, 2, 3):
+only = os.environ.get("EXP_ONLY")
+for W in ((64,) if only else (16, 64, 128)):
+    for streams in ((1, 2) if only else (1, 2, 3)):
         for n_ins, name in ((N_INSERT, "mixed"), (0, "search")):
             ms = cycles(W, streams, n_ins)
             ops = steps * W * (N_SEARCH + n_ins)
             print(json.dumps({"exp": "cycles", "W": W, "streams": streams, "kind": name, "steps": steps, "ms": round(ms, 3),
                               "Gops": round(ops / ms / 1e6, 2), "us_per_step": round(ms / steps * 1e3, 1)}), flush=True)
+if only:
+    sys.exit(0)
 # the round-1 shape for comparison: one search + one insert launch per batch, 64 streams, one graph
 res = N.BenchResult()
 for r in range(3):
