@@ -10,7 +10,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Imegakv_b200/csrc $(DEFS
             -Xcompiler -fPIC -Xcompiler -fno-exceptions -Xcompiler -fno-rtti -Xcompiler -Wall
 CSRC     := megakv_b200/csrc
 LIBDIR   := megakv_b200/lib
-OBJS     := $(LIBDIR)/libgpuhash.o $(LIBDIR)/gpuhash_index.o $(LIBDIR)/gpuhash_workload.o $(LIBDIR)/gpuhash_shard.o $(LIBDIR)/gpuhash_ring.o
+OBJS     := $(LIBDIR)/libgpuhash.o $(LIBDIR)/gpuhash_index.o $(LIBDIR)/gpuhash_workload.o $(LIBDIR)/gpuhash_shard.o $(LIBDIR)/gpuhash_xchg.o $(LIBDIR)/gpuhash_ring.o
 HDRS     := include/gpu_hash.h include/libgpuhash.h include/gpuhash_ex.h $(wildcard $(CSRC)/*.cuh)
 
 all: $(LIBDIR)/libgpuhash.so $(LIBDIR)/libgpuhash.a

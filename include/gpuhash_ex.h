@@ -315,6 +315,36 @@ int   gpuhash_ipc_export(void *dev_ptr, void *handle_out_64B);      /* cudaIpcGe
 void *gpuhash_ipc_import(const void *handle_64B);                   /* cudaIpcOpenMemHandle, NULL on failure */
 int   gpuhash_ipc_close(void *imported_ptr);
 
+/* ---- sharded index, ONE kernel per scheduler cycle (megakv_b200/csrc/gpuhash_xchg.cu) ----
+ * The routed path above as a software pipeline: launch j of a rank scatters its exchange j into the owners' inboxes,
+ * serves exchange j-1 (what the peers sent one launch ago: search -> delete -> insert per source, results straight into
+ * the origins' staging areas) and gathers exchange j-2 into its caller's search_out -- in ONE kernel whose warps take
+ * interleaved scatter / lookup / gather tiles by ticket, so the routing traffic hides under the lookups' line fills.
+ * Between GPUs there is one stream memory operation per launch (every peer's previous launch has raised its flag) and
+ * no wait inside any kernel.  One exchange = one scheduler cycle of the reference (all its workers' batches,
+ * src/mega_scheduler.c:393-504).  An xchg object owns a triple-buffered arena (inboxes, staging, routing maps, flags);
+ * the arenas of all ranks are made known to each other with gpuhash_xchg_set_peers (plain device pointers inside one
+ * process, CUDA IPC imports across processes: gpuhash_ipc_export / gpuhash_ipc_import on gpuhash_xchg_arena()).
+ *   gpuhash_xchg_step   COLLECTIVE in the number of calls: every rank calls it equally often (empty parts allowed).
+ *                       The buffers of call j may be device or pinned host memory; search_in/delete_in/insert_in must stay
+ *                       valid until launch j has run, search_out receives the results when launch j+2 has run.
+ *   gpuhash_xchg_flush  two steps without new requests: afterwards (and after synchronising the stream) every earlier
+ *                       exchange is complete and its results are in place.
+ *   gpuhash_xchg_error  0, a CUDA error, or -3 if a wait inside a kernel timed out.
+ * Sequence numbers are baked into the launches: a CUDA graph that captured steps may be replayed once. */
+typedef struct gpuhash_xchg_s gpuhash_xchg_t;
+gpuhash_xchg_t *gpuhash_xchg_create(const gpuhash_geom_t *g, void *table_d, uint32_t hash_mask_total, int log2_shards,
+		int my_rank, size_t cap_search, size_t cap_update);
+void    *gpuhash_xchg_arena(gpuhash_xchg_t *x, size_t *bytes);
+int      gpuhash_xchg_set_peers(gpuhash_xchg_t *x, const void *const *peer_arenas);
+int      gpuhash_xchg_set_stats(gpuhash_xchg_t *x, gpuhash_stats_t *stats_d);
+int      gpuhash_xchg_step(gpuhash_xchg_t *x, const void *search_in, size_t n_search, void *search_out,
+		const void *delete_in, size_t n_delete, const void *insert_in, size_t n_insert, void *stream);
+int      gpuhash_xchg_flush(gpuhash_xchg_t *x, void *stream);
+unsigned gpuhash_xchg_seq(const gpuhash_xchg_t *x);
+int      gpuhash_xchg_error(gpuhash_xchg_t *x);
+void     gpuhash_xchg_destroy(gpuhash_xchg_t *x);
+
 /* ---- synthetic request streams generated on the device (bench tooling; SURVEY.md 8(d) key stream) ----
  * inserts: keys first..first+n-1 of the splitmix64 stream `seed`, loc = key index + 1; either output may be NULL.
  * queries: n searches for keys drawn from the first `population` keys, uniformly (theta 0) or Zipf(theta)

@@ -148,6 +148,15 @@ SYMBOLS = {
     "gpuhash_ipc_export": (_i, [_vp, _vp]),
     "gpuhash_ipc_import": (_vp, [_vp]),
     "gpuhash_ipc_close": (_i, [_vp]),
+    "gpuhash_xchg_create": (_vp, [_gp, _vp, C.c_uint32, _i, _i, _sz, _sz]),
+    "gpuhash_xchg_arena": (_vp, [_vp, C.POINTER(_sz)]),
+    "gpuhash_xchg_set_peers": (_i, [_vp, _vp]),
+    "gpuhash_xchg_set_stats": (_i, [_vp, _vp]),
+    "gpuhash_xchg_step": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "gpuhash_xchg_flush": (_i, [_vp, _vp]),
+    "gpuhash_xchg_seq": (C.c_uint, [_vp]),
+    "gpuhash_xchg_error": (_i, [_vp]),
+    "gpuhash_xchg_destroy": (None, [_vp]),
     "gpuhash_gen_inserts": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, _vp]),
     "gpuhash_gen_queries": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
     "gpuhash_gen_requests": (_i, [_vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),

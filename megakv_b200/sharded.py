@@ -378,3 +378,128 @@ class LocalCluster:
 
     def error(self):
         return sum(b.p2p_error() for b in self.be)
+
+
+class ShardExchange:
+    """The sharded index as ONE kernel per scheduler cycle (megakv_b200/csrc/gpuhash_xchg.cu): launch j scatters
+    exchange j, serves exchange j-1 and gathers exchange j-2, tiles of the three interleaved by ticket; one stream
+    memory operation per launch is all the inter-GPU synchronisation.  Mirrors gpuhash_xchg_*.
+
+    step() is COLLECTIVE in the number of calls (every rank calls it equally often; any part may be empty).  The results
+    of the step issued as call j are in its `out` tensor once two more steps (or flush()) have run on the stream.
+    One exchange = one scheduler cycle of the reference: search -> delete -> insert (mega_scheduler.c:393-504)."""
+
+    def __init__(self, plan, rank, cap_search, cap_update, algo=0, layout=0, table=None):
+        import torch
+        from . import _native as N
+        from .hashindex import DeviceBuffer, make_geom
+        self.torch, self.N, self.L = torch, N, N.lib()
+        self.plan, self.rank, self.G = plan, rank, plan.world
+        self.geom = make_geom(plan.mem_p_total, algo, plan.log2, layout)
+        self.table = table if table is not None else DeviceBuffer(self.L.gpuhash_table_bytes(C.byref(self.geom)), zero=True)
+        self.x = self.L.gpuhash_xchg_create(C.byref(self.geom), self.table.ptr, plan.hash_mask_total, plan.log2, rank,
+                                            int(cap_search), int(cap_update))
+        if not self.x:
+            raise N.GpuHashError("gpuhash_xchg_create failed (arguments or device memory)")
+        nbytes = C.c_size_t()
+        self.arena = self.L.gpuhash_xchg_arena(self.x, C.byref(nbytes))
+        self.arena_bytes = nbytes.value
+        self._imports = []
+        self._keep = []                                         # tensors of the exchanges still in flight
+
+    def set_peers(self, arenas):
+        arr = (C.c_void_p * MAX_SHARDS)()
+        for k, v in enumerate(arenas):
+            arr[k] = v
+        self.N.check(self.L.gpuhash_xchg_set_peers(self.x, arr), "gpuhash_xchg_set_peers")
+
+    def connect(self, dist, group=None):
+        """exchange CUDA IPC handles of the arenas over the process group (one process per GPU)"""
+        t, L, N = self.torch, self.L, self.N
+        if self.G == 1:
+            return
+        handle = (C.c_ubyte * 64)()
+        N.check(L.gpuhash_ipc_export(self.arena, handle), "cudaIpcGetMemHandle")
+        dev = t.device("cuda", t.cuda.current_device())
+        mine = t.tensor(list(handle), dtype=t.uint8, device=dev)
+        allh = [t.empty_like(mine) for _ in range(self.G)]
+        dist.all_gather(allh, mine, group=group)
+        peers = []
+        for r in range(self.G):
+            if r == self.rank:
+                peers.append(self.arena)
+                continue
+            p = L.gpuhash_ipc_import((C.c_ubyte * 64)(*allh[r].cpu().tolist()))
+            if not p:
+                raise N.GpuHashError(f"cudaIpcOpenMemHandle failed for rank {r}")
+            self._imports.append(p)
+            peers.append(p)
+        dist.barrier(group=group)
+        self.set_peers(peers)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def step(self, search=None, out=None, delete=None, insert=None):
+        """search: int32 [n, 2] (sig, hash), out: int32 [n, 2]; delete / insert: int32 [n, 3] (sig, hash, loc); device or
+        pinned host tensors.  Returns `out` (allocated if missing) -- filled two steps later."""
+        ns = 0 if search is None else search.shape[0]
+        if ns and out is None:
+            out = self.torch.empty((ns, 2), dtype=self.torch.int32, device=search.device)
+        nd = 0 if delete is None else delete.shape[0]
+        ni = 0 if insert is None else insert.shape[0]
+        for x_ in (search, out, delete, insert):
+            assert x_ is None or (x_.is_contiguous() and x_.dtype == self.torch.int32)
+        self.N.check(self.L.gpuhash_xchg_step(self.x, search.data_ptr() if ns else None, ns, out.data_ptr() if ns else None,
+                                              delete.data_ptr() if nd else None, nd, insert.data_ptr() if ni else None, ni,
+                                              self._stream()), "gpuhash_xchg_step")
+        self._keep = self._keep[-2:] + [(search, out, delete, insert)]
+        return out
+
+    def flush(self):
+        self.N.check(self.L.gpuhash_xchg_flush(self.x, self._stream()), "gpuhash_xchg_flush")
+        self._keep = self._keep[-2:] + [None, None]
+
+    def error(self):
+        return self.L.gpuhash_xchg_error(self.x)
+
+    def close(self):
+        if self.x:
+            self.torch.cuda.synchronize()
+            for p in self._imports:
+                self.L.gpuhash_ipc_close(p)
+            self.L.gpuhash_xchg_destroy(self.x)
+            self.x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocalExchangeCluster:
+    """G virtual ranks of ShardExchange on ONE GPU in one process (plain device pointers as "peer" arenas): the kernel,
+    flags, slots and arena layout of the multi-process run minus NVLink.  One step() = launch j of every rank, issued
+    rank by rank on the current stream, which satisfies every flag by stream order."""
+
+    def __init__(self, plan, cap_search, cap_update, algo=0, layout=0, tables=None):
+        self.plan, self.G = plan, plan.world
+        self.xs = [ShardExchange(plan, r, cap_search, cap_update, algo, layout, table=tables[r] if tables else None) for r in range(self.G)]
+        for x in self.xs:
+            x.set_peers([y.arena for y in self.xs])
+
+    @property
+    def tables(self):
+        return [x.table for x in self.xs]
+
+    def step(self, searches=None, outs=None, deletes=None, inserts=None):
+        pick = lambda lst, r: None if lst is None else lst[r]
+        return [self.xs[r].step(pick(searches, r), pick(outs, r), pick(deletes, r), pick(inserts, r)) for r in range(self.G)]
+
+    def flush(self):
+        for _ in range(2):
+            self.step()
+
+    def error(self):
+        return sum(1 for x in self.xs if x.error() != 0)

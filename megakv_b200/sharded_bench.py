@@ -25,7 +25,7 @@ def main(args, rank, world, local_rank, log):
     import torch.distributed as dist
     import megakv_b200 as mk
     from megakv_b200 import _native as N
-    from megakv_b200.sharded import ShardPlan, ShardedIndex, CudaShardBackend
+    from megakv_b200.sharded import ShardPlan, ShardedIndex, CudaShardBackend, ShardExchange
     import bench as B
 
     torch.cuda.set_device(local_rank)
@@ -53,13 +53,21 @@ def main(args, rank, world, local_rank, log):
     # of the reference's triple-buffered batches, mega_batch.h:74-82).  One exchange routes the W batches of a scheduler
     # cycle at once -- what the reference's cycle does with the batches of all its workers (mega_scheduler.c:393-504).
     GROUP = W
-    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 8)), 16, steps))
+    # mode "xchg" (the product): ONE kernel per step and GPU (gpuhash_xchg.cu) -- launch j scatters exchange j, serves j-1,
+    # gathers j-2, tiles interleaved by ticket.  mode "lanes": the scatter / serve / gather kernels of gpuhash_shard.cu,
+    # S exchanges in flight on S streams (kept for A/B runs: GPUHASH_SHARD_MODE=lanes).
+    mode = os.environ.get('GPUHASH_SHARD_MODE', 'xchg')
+    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 8)), 16, steps)) if mode == 'lanes' else 1
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
-    lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)]
+    lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)] if mode == 'lanes' else []
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    split_updates = False
-    ulanes, ustreams = [], []
-    ixc = ShardedIndex(lanes[0].be, plan, exchange="collective")  # same table and buffers, NCCL exchange (baseline + independent checker)
+    ulanes = []
+    xch = None
+    if mode != 'lanes':
+        xch = ShardExchange(plan, rank, GROUP * N_SEARCH, GROUP * N_INSERT, table=be.table)
+        xch.connect(dist)
+    be_big = lanes[0].be if lanes else CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table)
+    ixc = ShardedIndex(be_big, plan, exchange="collective")       # same table, NCCL exchange (baseline + independent checker)
 
     # ---- preload through the routed insert path: rank r inserts key indices r*per_rank .. in chunks
     pop = (1 << plan.mem_p_total) // 8 // 4
@@ -104,6 +112,12 @@ def main(args, rank, world, local_rank, log):
                 index.search(sel_f[b * N_SEARCH:(b + W) * N_SEARCH], out_f[b * N_SEARCH:(b + W) * N_SEARCH])
                 if with_insert:
                     index.insert(ins_f[b * N_INSERT:(b + W) * N_INSERT])
+            return
+        if xch is not None:                                             # count + 2 launches: the pipeline fills and drains inside the region
+            for b in cycles_of(first, count):
+                xch.step(sel_f[b * N_SEARCH:(b + W) * N_SEARCH], out_f[b * N_SEARCH:(b + W) * N_SEARCH], None,
+                         ins_f[b * N_INSERT:(b + W) * N_INSERT] if with_insert else None)
+            xch.flush()
             return
         cur = torch.cuda.current_stream()
         for st in streams:
@@ -157,6 +171,8 @@ def main(args, rank, world, local_rank, log):
 
     def phase_profile(count=8):
         """one lane, call by call, CUDA events around every launch: where a routed step spends its time (us, this rank)"""
+        if not lanes:
+            return None
         lane, be_l = lanes[0], lanes[0].be
         names = ["search.scatter+publish", "search.serve", "search.gather", "insert.scatter+publish", "insert.serve"]
         acc = [0.0] * 5
@@ -194,7 +210,7 @@ def main(args, rank, world, local_rank, log):
                 fresh_inserts(); torch.cuda.synchronize()
     t_val = float(np.median(regions))
     value = world * steps * W * BATCH / t_val / 1e6
-    err = be.p2p_error() + sum(l.be.p2p_error() for l in lanes + ulanes)
+    err = be.p2p_error() + sum(l.be.p2p_error() for l in lanes + ulanes) + (abs(xch.error()) if xch else 0)
     assert err == 0, "a flag wait timed out"
     mism, orphans, checked = parity_of_step(warm + steps - 1)          # the last timed step, every rank, every word
     assert mism == 0, f"{mism} of {checked} routed searches returned something else than their key's location"
@@ -203,7 +219,7 @@ def main(args, rank, world, local_rank, log):
 
     if quick:
         if rank == 0:
-            B.emit({"quick": True, "n_gpus": world, "lanes": S, "group": GROUP, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
+            B.emit({"quick": True, "n_gpus": world, "mode": mode, "lanes": S, "group": GROUP, "graph": use_graph, "wait_mode": L.gpuhash_wait_mode(), "value_Mops": round(value, 1),
                     "per_gpu_Mops": round(value / world, 1), "regions_ms": [round(x * 1e3, 3) for x in regions],
                     "us_per_step": round(t_val / steps * 1e6, 2), "mismatches": mism, "orphans": orphans})
         dist.barrier(); dist.destroy_process_group()
@@ -234,6 +250,12 @@ def main(args, rank, world, local_rank, log):
         hi.copy_(ins_f[: ke * N_INSERT].cpu())
 
     def e2e_issue(count, zero_copy):
+        if xch is not None:                                             # the kernel reads the pinned request arrays and writes the pinned result array itself
+            for c in range(count):
+                b = (c * W) % ke
+                xch.step(hs[b * N_SEARCH:(b + W) * N_SEARCH], ho[b * N_SEARCH:(b + W) * N_SEARCH], None, hi[b * N_INSERT:(b + W) * N_INSERT])
+            xch.flush()
+            return
         cur = torch.cuda.current_stream()
         for st in streams:
             st.wait_stream(cur)
@@ -269,7 +291,7 @@ def main(args, rank, world, local_rank, log):
 
     e_steps = steps
     e2e_variants = {}
-    for zero_copy, name in ((1, "zero_copy+graph"), (0, "staged+graph")):
+    for zero_copy, name in ((1, "zero_copy+graph"), (0, "staged+graph")) if xch is None else ((1, "zero_copy+graph"),):
         g_ok = use_graph
         try:
             e2e(2, zero_copy, g_ok)                                     # warm-up
@@ -289,7 +311,7 @@ def main(args, rank, world, local_rank, log):
         log(f"e2e {name}: {e_steps} steps in {t_e * 1e3:.2f} ms (wall)")
     e2e_path = "zero_copy+graph" if "zero_copy+graph" in e2e_variants else "zero_copy"       # ONE fixed path is the headline
     e2e_val = e2e_variants[e2e_path]
-    assert be.p2p_error() + sum(l.be.p2p_error() for l in lanes) == 0, "a flag wait timed out"
+    assert be.p2p_error() + sum(l.be.p2p_error() for l in lanes) + (abs(xch.error()) if xch else 0) == 0, "a flag wait timed out"
 
     if rank == 0:
         peak, peak_src = B.peaks()
@@ -300,7 +322,11 @@ def main(args, rank, world, local_rank, log):
                            f"(2^{plan.mem_p_shard} per GPU), keys routed by the top {log2w} bucket-index bits over NVLink; "
                            f"one step = one scheduler cycle per GPU = ONE exchange of {W} batches of 64K signatures "
                            f"({N_SEARCH} searches + {N_INSERT} inserts each) per GPU")
-        cfg.update({"mem_p_total": plan.mem_p_total, "exchange": "peer stores + flags (fused)", "cuda_graph": use_graph, "lanes": S,
+        cfg.update({"mem_p_total": plan.mem_p_total, "cuda_graph": use_graph,
+                    "exchange": ("ONE kernel per step and GPU: scatter of exchange j, serve of j-1, gather of j-2 as interleaved tiles; "
+                                 "peer stores over NVLink, one stream mem-op wait per launch (gpuhash_xchg.cu)") if xch is not None
+                                else "peer stores + flags, scatter / serve / gather kernels over lanes (gpuhash_shard.cu)",
+                    "lanes": S,
                     "wait_mode": "stream mem-ops" if L.gpuhash_wait_mode() == 1 else "kernel",
                     "parallelism": f"shard{world}"})
         line = {
@@ -308,16 +334,17 @@ def main(args, rank, world, local_rank, log):
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(t_val / steps * 1e3, 6),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
             "timing": {"timed_region_ms": round(t_val * 1e3, 3), "regions_ms": [round(x * 1e3, 3) for x in regions],
-                       "what": f"each region = exactly {steps} steps (exchanges), CUDA events, max over ranks; median of {len(regions)} regions"},
+                       "what": f"each region = exactly {steps} steps (exchanges) start to finish" + (f" = {steps + 2} launches (pipeline fill and drain inside)" if xch is not None else "") + f", CUDA events, max over ranks; median of {len(regions)} regions"},
             "per_gpu_Mops": round(value / world, 1),
             "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": (8 * N_SEARCH + 12 * N_INSERT) * W,
                     "d2h_bytes_per_step": 8 * N_SEARCH * W, "steps": e_steps, "path": e2e_path, "variants": e2e_variants,
                     "timing": "host wall clock around the replay of the step graph + synchronize, max over ranks"},
-            "gpu_launches": steps * 5,                                   # per rank: scatter, serve, gather + insert scatter, serve per exchange
+            # per rank -- xchg: one kernel per step + the two that drain the pipeline; lanes: scatter, serve, gather + insert scatter, serve
+            "gpu_launches": steps + 2 if xch is not None else steps * 5,
             "parity_checked": True, "mismatches": mism, "searches_checked": checked, "orphaned_keys_seen": orphans,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "serve_search kernel (per GPU, routed)", "peak_source": peak_src,
-                         "note": "search path only, includes both NVLink exchanges"},
+                         "traffic": None, "kernel": ("xchg_step_kernel (per GPU: routing + lookups of one step)" if xch is not None else "serve_search kernel (per GPU, routed)"),
+                         "peak_source": peak_src, "note": "search path only, includes both NVLink exchanges"},
             "nccl_baseline": {"value": round(world * kb * W * BATCH / t_nccl / 1e6, 1), "unit": "Mops/s", "steps": kb,
                               "what": "same steps, exchanges through torch.distributed all_to_all_single"},
             "phase_us_one_lane": phases,
