@@ -355,6 +355,13 @@ int gpuhash_gen_queries(void *selem_d, void *expect_loc_d, uint64_t seed, uint64
 int gpuhash_gen_requests(void *ielem_d, uint64_t seed, uint64_t population, size_t n,
 		uint64_t rng_seed, double theta, double zetan, void *stream);   /* same draw as (sig, hash, loc) triples */
 
+/* the same with ranks drawn by the REFERENCE's generator, bit for bit (src/zipf.h:44-183: mehcached_zipf_next with its
+ * approximate pow and 48-bit LCG; what SURVEY.md 8(d) names for the zipf configs): elements first .. first+n-1 of the
+ * sequence seeded with rand_seed (< 2^48); theta in [0, 1); zetan = mehcached_zeta(population, theta).  triples != 0:
+ * (sig, hash, loc = rank + 1) records (insert / delete requests), else (sig, hash) searches. */
+int gpuhash_gen_requests_ref_zipf(void *out_d, void *expect_loc_d, uint64_t seed, uint64_t population, size_t n,
+		uint64_t rand_seed, uint64_t first, double theta, double zetan, int triples, void *stream);
+
 /* ---- timed loops (CUDA events on the launching streams; the Python bench only orchestrates) ---- */
 typedef struct gpuhash_bench_result_s {
 	float  total_ms;        /* first launch -> last completion, events */

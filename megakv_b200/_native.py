@@ -160,6 +160,7 @@ SYMBOLS = {
     "gpuhash_gen_inserts": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, _vp]),
     "gpuhash_gen_queries": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
     "gpuhash_gen_requests": (_i, [_vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_double, C.c_double, _vp]),
+    "gpuhash_gen_requests_ref_zipf": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _sz, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _i, _vp]),
     "gpuhash_bench_resident": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),
     "gpuhash_bench_e2e": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, C.POINTER(BenchResult)]),
     "gpuhash_bench_cycles": (_i, [_gp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, C.POINTER(BenchResult)]),

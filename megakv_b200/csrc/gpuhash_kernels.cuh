@@ -1294,15 +1294,28 @@ __device__ __forceinline__ void tiles_wait(const uint32_t* c, uint32_t target, c
 	__syncwarp();
 }
 
-// publish `count` finished tiles on counter ws[slot]: everything this warp read or wrote for them happens-before the add
+constexpr uint32_t kWsCounters = 32, kWsPerWorker = 16, kWsDelete = 8;     // word offsets inside the workspace
+// Publish `count` finished tiles on counter ws[slot].  What the waiters need ordered before their own table accesses:
+//   delete tiles   the CAS writes of the deletes                       -> fence, then add
+//   search tiles   nothing but the table READS of the searches, and those have returned their data before the warp gets
+//                  here (every lane consumed its rows to form the results; __syncwarp collects the lanes).  The result
+//                  stores are for the host / the next kernel, ordered by the kernel boundary.  So: no fence.  A fence here
+//                  waits for the warp's result stores to be acknowledged, once per claim: ncu (profiles/r02_xchg_ncu.md)
+//                  shows stall_membar as 12 % of a lookup warp's time.  -DGH_PUBLISH_FENCE_ALWAYS restores it for A/B runs.
 __device__ __forceinline__ void tiles_publish(uint32_t* ws, uint32_t slot, uint32_t& count, unsigned lane)
 {
 	if (count == 0) return;                               // warp-uniform
 	__syncwarp();
-	if (lane == 0) { __threadfence(); atomicAdd(ws + slot, count); }
+	if (lane == 0) {
+#ifdef GH_PUBLISH_FENCE_ALWAYS
+		__threadfence();
+#else
+		if (((slot - kWsCounters) & (kWsPerWorker - 1)) == kWsDelete) __threadfence();
+#endif
+		atomicAdd(ws + slot, count);
+	}
 	count = 0;
 }
-constexpr uint32_t kWsCounters = 32, kWsPerWorker = 16, kWsDelete = 8;     // word offsets inside the workspace
 __host__ __device__ inline size_t cycle_workspace_words(int max_batches) { return kWsCounters + (size_t)kWsPerWorker * (size_t)max_batches; }
 
 #ifndef GH_CYCLE_MIN_CTAS

@@ -75,6 +75,63 @@ __global__ void gen_queries_kernel(uint32_t *sel, uint32_t *expect_loc, uint64_t
 	}
 }
 
+/* ---- the reference's own rank generator, src/zipf.h:44-183, bit for bit (BASELINE configs[2] is quoted on it) ----
+ * Every double operation is an explicit round-to-nearest intrinsic: nvcc would otherwise contract a * b + c into one FMA,
+ * which rounds once where the host code the reference compiles to rounds twice. */
+__device__ __forceinline__ double ref_pow_approx(double a, double b)                  /* zipf.h:44-71 */
+{
+	int whole = (int)b;
+	int hi = __double2hiint(a);
+	hi = (int)__dadd_rn(__dmul_rn(__dsub_rn(b, (double)whole), (double)(hi - 1072632447)), 1072632447.);
+	const double frac = __hiloint2double(hi, 0);
+	double r = 1.;
+	for (; whole; whole >>= 1, a = __dmul_rn(a, a))
+		if (whole & 1) r = __dmul_rn(r, a);
+	return __dmul_rn(r, frac);
+}
+
+/* state i + 1 of the 48-bit LCG x <- a x + c (zipf.h:117-126) started at x0: the affine map raised to the power i + 1 by
+ * squaring, so that every thread draws its own element of the SAME sequence the sequential generator walks */
+__device__ __forceinline__ uint64_t ref_lcg_at(uint64_t x0, uint64_t steps)
+{
+	uint64_t ra = 1, rc = 0, a = 0x5deece66dULL, c = 0xbULL;
+	for (; steps; steps >>= 1) {
+		if (steps & 1) { ra = ra * a; rc = rc * a + c; }
+		c = c * a + c; a = a * a;
+	}
+	return (ra * x0 + rc) & ((1ULL << 48) - 1);
+}
+
+__global__ void gen_queries_ref_kernel(uint32_t *sel, uint32_t *expect_loc, uint64_t seed, uint64_t population,
+		size_t n, uint64_t rand_seed, uint64_t first, double theta, double zetan, int triples)
+{
+	double eta = 0, alpha = 0, thres = 0;
+	const double dbl_n = (double)population;
+	if (theta > 0.0) {                                                               /* zipf.h:94-97, 143-146 */
+		alpha = __ddiv_rn(1., __dsub_rn(1., theta));
+		thres = __dadd_rn(1., ref_pow_approx(0.5, theta));
+		const double zeta2 = __dadd_rn(__ddiv_rn(1., ref_pow_approx(1., theta)), __ddiv_rn(1., ref_pow_approx(2., theta)));
+		eta = __ddiv_rn(__dsub_rn(1., ref_pow_approx(__ddiv_rn(2., dbl_n), __dsub_rn(1., theta))), __dsub_rn(1., __ddiv_rn(zeta2, zetan)));
+	}
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const uint64_t x = ref_lcg_at(rand_seed, first + i + 1);
+		const double u = __ddiv_rn((double)x, (double)((1ULL << 48) - 1));
+		uint64_t idx;
+		if (theta == 0.0) idx = (uint64_t)__dmul_rn(dbl_n, u);                          /* :161-165 */
+		else {
+			const double uz = __dmul_rn(u, zetan);
+			if (uz < 1.0) idx = 0;
+			else if (uz < thres) idx = 1;
+			else idx = (uint64_t)__dmul_rn(dbl_n, ref_pow_approx(__dadd_rn(__dmul_rn(eta, __dsub_rn(u, 1.)), 1.), alpha));   /* :171-181 */
+		}
+		if (idx >= population) idx = population - 1;                                 /* (the reference would index past its key array) */
+		uint32_t sig, hash; key_to_req(key_at(seed, idx), sig, hash);
+		if (triples) { sel[3 * i] = sig; sel[3 * i + 1] = hash; sel[3 * i + 2] = (uint32_t)(idx + 1); }
+		else { sel[2 * i] = sig; sel[2 * i + 1] = hash; }
+		if (expect_loc) expect_loc[i] = (uint32_t)(idx + 1);
+	}
+}
+
 }  // namespace
 
 extern "C" int gpuhash_gen_inserts(void *ielem_d, void *selem_d, uint64_t seed, uint64_t first, size_t n, void *stream)
@@ -106,5 +163,19 @@ extern "C" int gpuhash_gen_requests(void *ielem_d, uint64_t seed, uint64_t popul
 	size_t blocks = (n + 255) / 256; if (blocks > 148 * 32) blocks = 148 * 32;
 	gen_queries_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t *)ielem_d, nullptr,
 			seed, population, n, rng_seed, theta, zetan, 1);
+	return (int)cudaGetLastError();
+}
+
+/* Requests for keys whose ranks come from the REFERENCE's generator (src/zipf.h: mehcached_zipf_next, approximate pow,
+ * 48-bit LCG seeded with rand_seed < 2^48), elements first .. first+n-1 of its sequence; theta in [0, 1), zetan as
+ * mehcached_zeta(n, theta) computes it (megakv_b200.keystream.ref_zetan).  triples != 0: (sig, hash, loc = rank + 1) records. */
+extern "C" int gpuhash_gen_requests_ref_zipf(void *out_d, void *expect_loc_d, uint64_t seed, uint64_t population, size_t n,
+		uint64_t rand_seed, uint64_t first, double theta, double zetan, int triples, void *stream)
+{
+	if (n == 0) return 0;
+	if (!out_d || population < 2 || theta < 0.0 || theta >= 1.0 || rand_seed >= (1ULL << 48) || (theta > 0.0 && !(zetan > 0.0))) return -1;
+	size_t blocks = (n + 255) / 256; if (blocks > 148 * 32) blocks = 148 * 32;
+	gen_queries_ref_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint32_t *)out_d, (uint32_t *)expect_loc_d,
+			seed, population, n, rand_seed, first, theta, zetan, triples);
 	return (int)cudaGetLastError();
 }

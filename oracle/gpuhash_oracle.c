@@ -279,6 +279,79 @@ void orc_keys_fill(uint64_t seed, uint64_t first_index, size_t n, orc_iel_t *iel
 	}
 }
 
+/* ------------------------------------------------- the reference's zipf key ranks */
+
+/* src/zipf.h:44-71: a^b for 0 <= b: the integer part of b by repeated squaring, the fractional part by scaling the
+ * exponent field of the double (high word minus the bias constant 1072632447, low word cleared). */
+static double zipf_pow(double a, double b)
+{
+	int whole = (int)b;
+	uint64_t bits; memcpy(&bits, &a, sizeof bits);
+	int32_t hi = (int32_t)(bits >> 32);
+	hi = (int32_t)((b - (double)whole) * (double)(hi - 1072632447) + 1072632447.);
+	bits = (uint64_t)(uint32_t)hi << 32;                      /* :56 low word = 0 */
+	double frac; memcpy(&frac, &bits, sizeof frac);
+	double r = 1.;
+	for (; whole; whole >>= 1, a *= a)                        /* :61-68 */
+		if (whole & 1) r *= a;
+	return r * frac;
+}
+
+/* src/zipf.h:117-126: 48-bit linear congruential step (the drand48 constants), scaled by 1 / (2^48 - 1) */
+static double zipf_rand(uint64_t *x)
+{
+	*x = (*x * 0x5deece66dULL + 0xbULL) & ((1ULL << 48) - 1);
+	return (double)*x / (double)((1ULL << 48) - 1);
+}
+
+/* src/zipf.h:73-115 (init) and :137-152 (the lazily computed constants): zetan = sum_{i=1..n} 1 / i^theta summed in
+ * ascending order with the approximate pow; theta == 0: uniform.  (theta == -1 "sequential" and theta >= 40 "always 0"
+ * of the reference are not workloads of this path.) */
+void orc_zipf_init(orc_zipf_t *z, uint64_t n, double theta, uint64_t rand_seed)
+{
+	memset(z, 0, sizeof *z);
+	z->n = n; z->theta = theta; z->rand_state = rand_seed; z->dbl_n = (double)n;
+	if (theta > 0. && theta < 1.) {
+		z->alpha = 1. / (1. - theta);
+		z->thres = 1. + zipf_pow(0.5, theta);
+		double sum = 0.;
+		for (uint64_t i = 0; i < n; i++) sum += 1. / zipf_pow((double)i + 1., theta);          /* :103-115 */
+		z->zetan = sum;
+		double zeta2 = 0.;
+		for (uint64_t i = 0; i < 2; i++) zeta2 += 1. / zipf_pow((double)i + 1., theta);
+		z->eta = (1. - zipf_pow(2. / (double)n, 1. - theta)) / (1. - zeta2 / sum);               /* :145-146 */
+	}
+}
+
+/* a state whose zetan is already known (2^29 terms take seconds; the bench computes it once) */
+void orc_zipf_init_zetan(orc_zipf_t *z, uint64_t n, double theta, uint64_t rand_seed, double zetan)
+{
+	memset(z, 0, sizeof *z);
+	z->n = n; z->theta = theta; z->rand_state = rand_seed; z->dbl_n = (double)n;
+	z->alpha = 1. / (1. - theta);
+	z->thres = 1. + zipf_pow(0.5, theta);
+	z->zetan = zetan;
+	double zeta2 = 0.;
+	for (uint64_t i = 0; i < 2; i++) zeta2 += 1. / zipf_pow((double)i + 1., theta);
+	z->eta = (1. - zipf_pow(2. / (double)n, 1. - theta)) / (1. - zeta2 / zetan);
+}
+
+/* src/zipf.h:161-182: Gray et al.'s inversion; ranks 0 and 1 by thresholds, the rest by the power law */
+uint64_t orc_zipf_next(orc_zipf_t *z)
+{
+	double u = zipf_rand(&z->rand_state);
+	if (z->theta == 0.) return (uint64_t)(z->dbl_n * u);                                       /* :161-165 */
+	double uz = u * z->zetan;
+	if (uz < 1.) return 0;
+	if (uz < z->thres) return 1;
+	return (uint64_t)(z->dbl_n * zipf_pow(z->eta * (u - 1.) + 1., z->alpha));
+}
+
+void orc_zipf_fill(orc_zipf_t *z, size_t n, uint64_t *ranks)
+{
+	for (size_t i = 0; i < n; i++) ranks[i] = orc_zipf_next(z);
+}
+
 /* ------------------------------------------------------- threaded baseline */
 
 double orc_now_sec(void)

@@ -90,6 +90,15 @@ void     orc_table_digest(const void *table, const orc_geom_t *g, int per_bucket
 /* key stream of SURVEY.md 8(d): key_i = i-th output (i from 0) of splitmix64
  * started at state `seed`; sig = low 32 bits (0 -> 1), hash = high 32 bits,
  * loc = first_index + i + 1. */
+/* the reference's key-rank generator (src/zipf.h:26-183, Gray et al. with an approximate pow and a 48-bit LCG),
+ * restated; pinned to vectors recorded from zipf.h itself (tests/golden/zipf_ref.npz, tests/golden/make_zipf_golden.py) */
+typedef struct orc_zipf_s {
+	uint64_t n; double theta, alpha, thres, dbl_n, zetan, eta; uint64_t rand_state;
+} orc_zipf_t;
+void     orc_zipf_init(orc_zipf_t *z, uint64_t n, double theta, uint64_t rand_seed);
+void     orc_zipf_init_zetan(orc_zipf_t *z, uint64_t n, double theta, uint64_t rand_seed, double zetan);
+uint64_t orc_zipf_next(orc_zipf_t *z);
+void     orc_zipf_fill(orc_zipf_t *z, size_t n, uint64_t *ranks);
 uint64_t orc_splitmix64(uint64_t *state);
 void     orc_keys_fill(uint64_t seed, uint64_t first_index, size_t n,
 		orc_iel_t *iel /* may be NULL */, orc_sel_t *sel /* may be NULL */);

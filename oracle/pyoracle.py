@@ -74,6 +74,9 @@ def lib():
         L.orc_pool_insert.argtypes = [vp, vp, gp, vp, sz]
         L.orc_pool_preload.argtypes = [vp, vp, gp, u64, u64, u64]
         L.orc_gen_queries.argtypes = [u64, u64, sz, u64, vp]
+        L.orc_zipf_init.argtypes = [vp, u64, C.c_double, u64]
+        L.orc_zipf_init_zetan.argtypes = [vp, u64, C.c_double, u64, C.c_double]
+        L.orc_zipf_fill.argtypes = [vp, sz, vp]
         _lib = L
     return _lib
 
@@ -183,6 +186,31 @@ class Pool:
 
     def preload(self, orc, seed, first, count):
         self.L.orc_pool_preload(self.h, _ptr(orc.table), C.byref(orc.g), seed, first, count)
+
+
+class ZipfState(C.Structure):                 # orc_zipf_t
+    _fields_ = [("n", C.c_uint64), ("theta", C.c_double), ("alpha", C.c_double), ("thres", C.c_double), ("dbl_n", C.c_double),
+                ("zetan", C.c_double), ("eta", C.c_double), ("rand_state", C.c_uint64)]
+
+
+class Zipf:
+    """the reference's key-rank generator (src/zipf.h:73-183) as restated in gpuhash_oracle.c"""
+
+    def __init__(self, n, theta, rand_seed, zetan=None):
+        self.st = ZipfState()
+        if zetan is None:
+            lib().orc_zipf_init(C.byref(self.st), n, theta, rand_seed)
+        else:
+            lib().orc_zipf_init_zetan(C.byref(self.st), n, theta, rand_seed, zetan)
+
+    @property
+    def zetan(self):
+        return self.st.zetan
+
+    def ranks(self, m):
+        out = np.empty(m, dtype=np.uint64)
+        lib().orc_zipf_fill(C.byref(self.st), m, _ptr(out))
+        return out
 
 
 def gen_queries(seed, population, n, rng_seed):

@@ -97,6 +97,21 @@ def main():
     t = min(timed(steps, False) for _ in range(2))
     res["search_us_per_rank_step"] = round(t / steps / G * 1e6, 1)
     res["search_Mops_per_gpu"] = round(steps * n_s / (t / G) / 1e6, 1)
+    # each kind of work alone: a step with requests followed by two without -> launch 1 only scatters, 2 only serves, 3 only gathers
+    if G == 1:
+        acc = [0.0, 0.0, 0.0]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        rounds = 5
+        for i in range(rounds):
+            torch.cuda.synchronize()
+            ev[0].record(); cl.step(sel[i % R], out[i % R])
+            ev[1].record(); cl.step()
+            ev[2].record(); cl.step()
+            ev[3].record(); torch.cuda.synchronize()
+            if i:
+                for k in range(3):
+                    acc[k] += ev[k].elapsed_time(ev[k + 1]) * 1e3 / (rounds - 1)
+        res["alone_us"] = {"scatter": round(acc[0], 1), "serve_search": round(acc[1], 1), "gather": round(acc[2], 1)}
     bad = 0
     for k in range(min(R, steps)):
         for r in range(G):
