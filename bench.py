@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own search kernel (oracle/_ref)")
     ap.add_argument("--no-ring", action="store_true", help="skip the persistent-kernel ring variant of the e2e leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[3] legs")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3],
+                    help="BASELINE configs[2] (two-choice, zipf, L2-resident vs HBM) and configs[3] (cuckoo churn at 90 %% load) are extra "
+                         "keys of the line (config2, config3); 2 or 3 runs only that one of the two")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

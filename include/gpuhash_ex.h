@@ -60,6 +60,9 @@ typedef struct gpuhash_stats_s {
 int    gpuhash_geom_init(gpuhash_geom_t *g, int mem_p, unsigned algo);
 /* shard `log2_shards` of a logical 2^mem_p_total-byte table: local table is 2^(mem_p_total-log2_shards) bytes */
 int    gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int log2_shards, unsigned algo);
+/* gpuhash_geom_init + the layout that suits the table on the current device: PAIRS, except REFERENCE for a two-choice table
+ * that fits in L2 (cudaDevAttrL2CacheSize), where L2 sectors -- not DRAM line fills -- are the cost of a probe */
+int    gpuhash_geom_init_auto(gpuhash_geom_t *g, int mem_p, unsigned algo);
 size_t gpuhash_table_bytes(const gpuhash_geom_t *g);
 /* in-place rewrite of a table from g->layout to to_layout (async on stream); the caller then sets g->layout */
 int    gpuhash_table_convert(const gpuhash_geom_t *g, void *table_d, unsigned to_layout, void *stream);

@@ -64,6 +64,7 @@ SYMBOLS = {
     # gpuhash_ex.h
     "gpuhash_geom_init": (_i, [_gp, _i, _u]),
     "gpuhash_geom_init_shard": (_i, [_gp, _i, _i, _u]),
+    "gpuhash_geom_init_auto": (_i, [_gp, _i, _u]),
     "gpuhash_table_bytes": (_sz, [_gp]),
     "gpuhash_table_convert": (_i, [_gp, _vp, _u, _vp]),
     "gpuhash_set_default_geom": (None, [_gp]),

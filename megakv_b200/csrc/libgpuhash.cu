@@ -125,6 +125,19 @@ extern "C" int gpuhash_geom_init(gpuhash_geom_t *g, int mem_p, unsigned algo)
 	return gpuhash_geom_init_shard(g, mem_p, 0, algo);
 }
 
+/* gpuhash_geom_init with the layout chosen for the table: {sig, loc} pairs (every commit one 64-bit CAS; the fewest L2
+ * requests per probe beyond L2) unless the table is L2-resident AND the policy is two-choice -- then the reference's own
+ * byte layout, whose one-thread search reads the signature rows and, on a hit only, the location word: fewest L2 sectors,
+ * which is what an L2-resident table pays for (76 vs 67 Gops/s at MEM_P 26).  Cuckoo tables keep the pair
+ * layout at any size: only there an eviction chain re-homes a (sig, loc) pair atomically under concurrent inserts. */
+extern "C" int gpuhash_geom_init_auto(gpuhash_geom_t *g, int mem_p, unsigned algo)
+{
+	int rc = gpuhash_geom_init_shard(g, mem_p, 0, algo);
+	if (rc) return rc;
+	if (algo == GPUHASH_2CHOICE && gpuhash_table_bytes(g) <= l2_bytes_now()) g->layout = GPUHASH_LAYOUT_REFERENCE;
+	return 0;
+}
+
 extern "C" int gpuhash_geom_init_shard(gpuhash_geom_t *g, int mem_p_total, int log2_shards, unsigned algo)
 {
 	/* BUC_P = 6, IBLOCK_P = 3 (gpu_hash.h:57,67).  hash_t is 32 bits => at most 2^32 buckets, MEM_P <= 38;

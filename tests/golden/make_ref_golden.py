@@ -181,6 +181,72 @@ def case_delete(algo, mem_p, seed):
          table_in=t.reshape(-1), dele=dele.view(np.uint32), table=r.dump())
 
 
+def sparse(table_words):
+    """(indices of the non-empty buckets, their 16 words): what a mostly empty table of 2^20 .. 2^26 bytes is stored as"""
+    t = np.asarray(table_words, dtype=np.uint32).reshape(-1, 16)
+    idx = np.nonzero(t.any(axis=1))[0].astype(np.uint32)
+    return idx, t[idx].copy()
+
+
+def bucket2_of(mem_p, hash_, sig):
+    """gpu_hash.cu:66-67 with the geometry macros of gpu_hash.h:57-69 (only used to AIM probes; the answers come from the kernels)"""
+    hm = (1 << (mem_p - 6)) - 1; bm = (1 << (mem_p - 9)) - 1
+    return ((((hash_ ^ sig) & bm) | (hash_ & ~bm)) & hm).astype(np.uint32)
+
+
+def case_search_sparse(algo, mem_p, seed, nbuckets=20000):
+    """gpu_hash_search at a larger geometry (BLOCK_HASH_MASK of 11 / 17 bits) on a sparse hand-built table: keys that sit in
+    bucket 1 of their probe, keys that sit in the ALTERNATE bucket of their probe, duplicate signatures, misses"""
+    rng = np.random.default_rng(seed)
+    nb = 1 << (mem_p - 6)
+    t = np.zeros((nb, 2, 8), dtype=np.uint32)
+    n1 = nbuckets // 2
+    b = rng.choice(nb, size=n1, replace=False)
+    fill = rng.random((n1, 8)) < 0.6
+    t[b, 0, :] = np.where(fill, rng.integers(1, 2**32, (n1, 8), dtype=np.uint64).astype(np.uint32), 0)
+    t[b, 1, :] = rng.integers(1, 2**32, (n1, 8), dtype=np.uint64).astype(np.uint32)
+    # probes whose key sits in bucket 1
+    pl = rng.integers(0, 8, n1)
+    sel1 = np.empty(n1, dtype=SEL_DT); sel1["sig"] = t[b, 0, pl]; sel1["hash"] = b | (rng.integers(0, 2**32 >> (mem_p - 6), n1) << (mem_p - 6)).astype(np.uint32)
+    # keys placed into the alternate bucket of their probe: choose (hash, sig), put sig into slot sig & 7 of bucket2
+    n2 = nbuckets - n1
+    h2 = rng.integers(0, 2**32, n2, dtype=np.uint64).astype(np.uint32); s2 = rng.integers(1, 2**32, n2, dtype=np.uint64).astype(np.uint32)
+    b2 = bucket2_of(mem_p, h2, s2)
+    t[b2, 0, s2 & 7] = s2; t[b2, 1, s2 & 7] = rng.integers(1, 2**32, n2, dtype=np.uint64).astype(np.uint32)
+    sel2 = np.empty(n2, dtype=SEL_DT); sel2["sig"], sel2["hash"] = s2, h2
+    miss = np.empty(1000, dtype=SEL_DT)
+    miss["sig"] = rng.integers(1, 2**32, 1000, dtype=np.uint64); miss["hash"] = rng.integers(0, 2**32, 1000, dtype=np.uint64)
+    sel = np.concatenate([sel1, sel2, miss]); sel = sel[sel["sig"] != 0]
+    r = RefLib(algo, mem_p); r.load(t.reshape(-1))
+    idx, rows = sparse(t.reshape(-1))
+    save(f"ref_search_sparse_{algo}_{mem_p}", kind=np.array("search_sparse"), algo=np.array(algo), mem_p=np.array(mem_p),
+         bucket_idx=idx, bucket_rows=rows, sel=sel.view(np.uint32), out=r.search(sel))
+
+
+def case_serial_sparse(algo, mem_p, seed, nkeys=6000):
+    """gpu_hash_insert with ONE request per launch at a larger geometry: the keys' first buckets are 64 per block (512 buckets,
+    4096 slots for 6000 keys), so bucket 1 overflows, alternates spread over the whole block, and the cuckoo chains / two-choice
+    overwrites run under an 11 / 17-bit BLOCK_HASH_MASK; then a delete launch per key for a third of them"""
+    rng = np.random.default_rng(seed)
+    nb = 1 << (mem_p - 6)
+    r = RefLib(algo, mem_p)
+    iel = reqs(rng, nkeys)
+    block = rng.integers(0, 8, nkeys).astype(np.uint32) * np.uint32(nb // 8)
+    iel["hash"] = (block | rng.integers(0, 64, nkeys).astype(np.uint32)) | (rng.integers(0, 2**32 >> (mem_p - 6), nkeys) << (mem_p - 6)).astype(np.uint32)
+    # alternates must collide too, or nothing is ever evicted: keep the low signature bits small so bucket 2 stays near bucket 1
+    iel["sig"] = (iel["sig"] & np.uint32(~((1 << (mem_p - 9)) - 1) & 0xFFFFFFFF)) | rng.integers(1, 128, nkeys).astype(np.uint32)
+    r.insert_one_by_one(iel)
+    after_insert = r.dump()
+    dele = iel[::3]
+    for k in range(len(dele)):
+        r.delete(dele[k:k + 1])
+    probe = np.concatenate([to_sel(iel), to_sel(reqs(rng, 200))])
+    i1, r1 = sparse(after_insert); i2, r2 = sparse(r.dump())
+    save(f"ref_serial_sparse_{algo}_{mem_p}", kind=np.array("serial_sparse"), algo=np.array(algo), mem_p=np.array(mem_p),
+         iel=iel.view(np.uint32), dele=dele.view(np.uint32), sel=probe.view(np.uint32),
+         insert_idx=i1, insert_rows=r1, final_idx=i2, final_rows=r2, out=r.search(probe))
+
+
 if __name__ == "__main__":
     mk.require_gpu()
     only = sys.argv[1:] or ["search", "delete", "batch", "serial"]
@@ -193,4 +259,8 @@ if __name__ == "__main__":
     if "serial" in only:
         case_serial("cuckoo", 16, 0.5, 5, "half"); case_serial("cuckoo", 16, 0.97, 6, "full")
         case_serial("2choice", 16, 0.97, 7, "full")
+    if "sparse" in only or not sys.argv[1:]:
+        for mp in (20, 26):
+            case_search_sparse("cuckoo", mp, 10 + mp); case_search_sparse("2choice", mp, 11 + mp)
+            case_serial_sparse("cuckoo", mp, 12 + mp); case_serial_sparse("2choice", mp, 13 + mp)
     print("done")

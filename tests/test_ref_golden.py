@@ -24,6 +24,13 @@ def load(path):
     return g, str(g["kind"]), ALGO[str(g["algo"])], int(g["mem_p"])
 
 
+def dense(mem_p, idx, rows):
+    """a sparse vector (non-empty buckets only: MEM_P 20 and 26 tables are mostly zeros) as the full table, reference layout"""
+    t = np.zeros(((1 << mem_p) // 64, 16), dtype=np.uint32)
+    t[idx] = rows
+    return t.reshape(-1)
+
+
 def test_reference_vectors_are_present():
     kinds = {str(np.load(f)["kind"]) for f in FILES}
     assert {"search", "delete"} <= kinds, "reference-kernel vectors missing (tests/golden/make_ref_golden.py)"
@@ -61,6 +68,16 @@ def test_oracle_reproduces_reference_kernels(path):
             if it % 2:
                 o.delete(iel[: n // 2])
             assert o.digest(table=g["tables"][it]) == o.digest()
+    elif kind == "search_sparse":                                       # BLOCK_HASH_MASK of 11 / 17 bits through the reference's kernel
+        o = po.Oracle(mem_p, algo, table=dense(mem_p, g["bucket_idx"], g["bucket_rows"]))
+        assert np.array_equal(o.search(g["sel"].view(po.SEL_DT)), g["out"])
+    elif kind == "serial_sparse":                                       # one request per reference launch, overflowing first buckets
+        o = po.Oracle(mem_p, algo)
+        o.insert(g["iel"].view(po.IEL_DT))
+        assert np.array_equal(o.table, dense(mem_p, g["insert_idx"], g["insert_rows"])), "table bytes after the sequential inserts"
+        o.delete(g["dele"].view(po.IEL_DT))
+        assert np.array_equal(o.table, dense(mem_p, g["final_idx"], g["final_rows"])), "table bytes after the deletes"
+        assert np.array_equal(o.search(g["sel"].view(po.SEL_DT)), g["out"])
     else:
         pytest.fail(f"unknown kind {kind}")
 
@@ -87,6 +104,15 @@ def test_cuda_path_reproduces_reference_kernels(gpu, path, layout):
     elif kind == "serial":
         gpu_insert(t, g["iel"].view(mk.IEL_DT), flags=mk.INSERT_SERIAL)
         assert np.array_equal(t.dump_reference(), g["table"])
+        assert np.array_equal(gpu_search(t, g["sel"].view(mk.SEL_DT), prezero=False), g["out"])
+    elif kind == "search_sparse":
+        t.load_reference(dense(mem_p, g["bucket_idx"], g["bucket_rows"]))
+        assert np.array_equal(gpu_search(t, g["sel"].view(mk.SEL_DT), prezero=False), g["out"])
+    elif kind == "serial_sparse":
+        gpu_insert(t, g["iel"].view(mk.IEL_DT), flags=mk.INSERT_SERIAL)
+        assert np.array_equal(t.dump_reference(), dense(mem_p, g["insert_idx"], g["insert_rows"]))
+        gpu_delete(t, g["dele"].view(mk.IEL_DT))
+        assert np.array_equal(t.dump_reference(), dense(mem_p, g["final_idx"], g["final_rows"]))
         assert np.array_equal(gpu_search(t, g["sel"].view(mk.SEL_DT), prezero=False), g["out"])
     elif kind == "batch":
         o = po.Oracle(mem_p, algo)

@@ -61,3 +61,12 @@ def test_device_zipf_equals_the_reference_generator(gpu, k):
         ref_sel, _ = ks.ref_zipf_queries(1, n, 64, theta, seed, zetan if theta > 0 else None)
         if first == 0:
             assert np.array_equal(reqs[:64, 0], ref_sel["sig"]) and np.array_equal(reqs[:64, 1], ref_sel["hash"])
+
+
+def test_committed_zetan_table_is_what_the_restatement_computes():
+    """megakv_b200/zetan_table.json saves bench.py the 2^29-term sum; its small entries are re-derived here"""
+    import json
+    tab = json.load(open(os.path.join(os.path.dirname(ks.__file__), "zetan_table.json")))
+    for n in (1 << 21, 1 << 23):
+        assert float(tab["zetan"][str(n)]) == ks.ref_zetan(n, tab["theta"])
+    assert float(tab["zetan"][str(1 << 21)]) == po.Zipf(1 << 21, tab["theta"], 0).zetan
