@@ -15,6 +15,21 @@
  *   - the unused selem_shared_t / UNIT_THREAD_NUM leftovers are still declared
  *     so that old code keeps compiling.
  *
+ *   - INSIDE A BUCKET the library is free to order the 16 words differently
+ *     from bucket_t: the reference's callers only allocate and zero-fill the
+ *     table (mega_scheduler.c:273-274) and never read or write its bytes, and
+ *     all-zero means empty in every layout.  By default the library keeps slot
+ *     l as the pair {sig, loc} at words 2l, 2l+1 (one 64-bit CAS per commit)
+ *     instead of bucket_t's sig[8] then loc[8].  A host that DOES build or read
+ *     table images through bucket_t (libgpuhash/test/back/py_search_stream.c:
+ *     104-121) must select the reference byte layout: build the library with
+ *     -DGPUHASH_DEFAULT_LAYOUT_REFERENCE, or call gpuhash_set_default_geom()
+ *     with layout = GPUHASH_LAYOUT_REFERENCE, or convert with
+ *     gpuhash_table_convert() / gpuhash_index_load() / gpuhash_index_dump().
+ *   - the caller's MEM_P must be the library's: the three legacy calls take no
+ *     size, so a table smaller than the library's HT_SIZE is written out of
+ *     bounds exactly as with the reference (whose MEM_P is compiled in too).
+ *
  * The values baked in here are only the *defaults* of the three legacy entry
  * points in libgpuhash.h; the extended API (gpuhash_ex.h) takes the geometry
  * at run time.

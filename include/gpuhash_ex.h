@@ -33,7 +33,13 @@ extern "C" {
 /* table layouts.  The caller of the legacy ABI never interprets table bytes (mega_scheduler.c:273-274 only
  * allocates and zero-fills), so the layout is the library's choice; all-zero == empty in both.
  *   PAIRS      slot l = 8-byte {sig, loc} at byte 8*l of the 64 B bucket: (sig, loc) changes are one 64-bit CAS
- *   REFERENCE  bucket_t of gpu_hash.h:79-82 (sig[8] then loc[8]); for callers that memcpy tables in that layout */
+ *   REFERENCE  bucket_t of gpu_hash.h:79-82 (sig[8] then loc[8]); for callers that memcpy tables in that layout.
+ *              A commit is then two steps -- CAS on the signature word, store / exchange of the location word -- the
+ *              reference's own publication window: two cuckoo evictions that hit one slot back to back (launches of
+ *              several streams, or one launch at high load) can each carry the other's location on, leaving a
+ *              (sig, loc) mismatch.  The reference excludes that by running one CUDA block per insert partition; this
+ *              library runs grid-wide.  Use PAIRS for any table that takes concurrent cuckoo inserts at load factors
+ *              where evictions happen; REFERENCE is exact for searches, deletes, two-choice and low-load inserts. */
 #define GPUHASH_LAYOUT_PAIRS      0u
 #define GPUHASH_LAYOUT_REFERENCE  1u
 
@@ -239,7 +245,11 @@ int gpuhash_index_wait(gpuhash_index_t *ix, int ticket);
  * search -> delete -> insert (the reference's per-stream order, mega_scheduler.c:392-502); rings are unordered against
  * each other.  The kernel parks itself after idle_ms without a doorbell (default 2000) and is relaunched on demand.
  * One ring object per device at a time; the calls of one ring object come from one host thread (the scheduler thread of
- * the reference, src/mega.c:410) -- there is no locking inside. */
+ * the reference, src/mega.c:410) -- there is no locking inside.
+ * While the kernel is resident, anything that synchronises the whole DEVICE (cudaDeviceSynchronize, cudaFree, and so
+ * gpuhash_index_sync / _stats / _dump / _clear and gpuhash_dev_free) blocks until the kernel parks itself (idle_ms):
+ * call gpuhash_ring_park first.  Submit and wait notice a parked kernel, also one that parked with batches pending, and
+ * relaunch it. */
 typedef struct gpuhash_ring_s gpuhash_ring_t;
 gpuhash_ring_t *gpuhash_ring_create(const gpuhash_geom_t *g, void *table_d, int rings, int slots, int ctas_per_sm, unsigned idle_ms);
 long long gpuhash_ring_submit(gpuhash_ring_t *q, int ring,

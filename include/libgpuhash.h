@@ -20,6 +20,9 @@
  *   - num_thread / threads_per_blk are launch-shape hints of the old kernels;
  *     they are accepted (any value the reference accepted, and the ones its
  *     16-bit rounding bug broke) and otherwise ignored.
+ *   - the table's bytes belong to the library: slots are kept as {sig, loc}
+ *     pairs inside each 64 B bucket unless the reference byte layout is selected
+ *     (see gpu_hash.h); hosts that memcpy bucket_t images must select it;
  *   - geometry (MEM_P) and policy (HASH_CUCKOO / HASH_2CHOICE) default to the
  *     values of gpu_hash.h this header is compiled with by the LIBRARY; use
  *     gpuhash_set_default_geom() from gpuhash_ex.h to change them at run time.

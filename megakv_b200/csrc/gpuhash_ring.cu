@@ -376,6 +376,18 @@ extern "C" void gpuhash_ring_destroy(gpuhash_ring_t *q)
 /* One scheduler cycle of one worker: same arguments as gpuhash_index_submit, buffers PINNED (cudaHostAlloc /
  * cudaHostRegister).  Returns the batch number (> 0) to wait for, or a negative error.  Blocks only while the ring is
  * full (the slot's previous batch not completed). */
+/* The kernel parks itself (idle timeout, gpuhash_ring_park) at a batch boundary, possibly with batches still pending.
+ * Whoever finds the parked flag while waiting for one of them lets the kernel finish its exit and launches it again: it
+ * resumes at the first batch without a completion mark.  0, or a CUDA / launch error. */
+static int ring_relaunch_if_parked(gpuhash_ring_t *q)
+{
+	if (q->running && !__atomic_load_n(&q->flags_h[1], __ATOMIC_ACQUIRE)) return 0;
+	cudaError_t e = cudaStreamSynchronize(q->stream);
+	if (e != cudaSuccess) return (int)e;
+	q->running = 0;
+	return ring_launch(q);
+}
+
 extern "C" long long gpuhash_ring_submit(gpuhash_ring_t *q, int ring,
 		const void *search_in_h, size_t n_search, void *search_out_h,
 		const void *delete_in_h, size_t n_delete, const void *insert_in_h, size_t n_insert)
@@ -383,19 +395,16 @@ extern "C" long long gpuhash_ring_submit(gpuhash_ring_t *q, int ring,
 	if (!q || ring < 0 || ring >= q->rings || n_search > 0xffffffffu || n_delete > 0xffffffffu || n_insert > 0xffffffffu) return -1;
 	if ((n_search && (!search_in_h || !search_out_h)) || (n_delete && !delete_in_h) || (n_insert && !insert_in_h)) return -1;
 	if (((uintptr_t)search_in_h | (uintptr_t)search_out_h) & 7u) return -1;
-	if (!q->running || __atomic_load_n(&q->flags_h[1], __ATOMIC_ACQUIRE)) {   /* parked (idle timeout or gpuhash_ring_park) */
-		cudaError_t e = cudaStreamSynchronize(q->stream);                 /* the kernel is on its way out: let it finish */
-		if (e != cudaSuccess) return -(long long)e;
-		q->running = 0;
-		int rc = ring_launch(q);
-		if (rc) return -(long long)(rc > 0 ? rc : -rc);
-	}
+	int rc = ring_relaunch_if_parked(q);                                 /* parked (idle timeout or gpuhash_ring_park): start it again */
+	if (rc) return -(long long)(rc > 0 ? rc : -rc);
 	const uint32_t b = q->next[ring];
 	RingDesc *d = q->desc_h + (size_t)ring * q->slots + (b - 1) % q->slots;
 	if (b > (uint32_t)q->slots) {                                        /* slot still in flight? */
 		const double t0 = wall_ms();
 		while (__atomic_load_n(&d->done, __ATOMIC_ACQUIRE) != b - (uint32_t)q->slots) {
 			if (wall_ms() - t0 > 10000.0) return -2;
+			/* the kernel may have parked with this very slot pending: without a relaunch nothing would ever complete it */
+			if ((rc = ring_relaunch_if_parked(q)) != 0) return -(long long)(rc > 0 ? rc : -rc);
 		}
 	}
 	d->search_in = search_in_h; d->search_out = search_out_h; d->delete_in = delete_in_h; d->insert_in = insert_in_h;
@@ -426,13 +435,8 @@ extern "C" int gpuhash_ring_wait(gpuhash_ring_t *q, int ring, long long ticket, 
 		const uint32_t done = __atomic_load_n(&d->done, __ATOMIC_ACQUIRE);
 		if ((int32_t)(done - (uint32_t)ticket) >= 0) return 0;
 		if (timeout_ms && wall_ms() - t0 > (double)timeout_ms) return -2;
-		if (__atomic_load_n(&q->flags_h[1], __ATOMIC_ACQUIRE)) {                 /* the kernel parked with this batch pending */
-			cudaError_t e = cudaStreamSynchronize(q->stream);
-			if (e != cudaSuccess) return (int)e;
-			q->running = 0;
-			int rc = ring_launch(q);                                             /* it resumes at the first incomplete batch */
-			if (rc) return rc;
-		}
+		int rc = ring_relaunch_if_parked(q);                                     /* the kernel parked with this batch pending */
+		if (rc) return rc;
 	}
 }
 
