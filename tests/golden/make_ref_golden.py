@@ -190,8 +190,8 @@ def sparse(table_words):
 
 def bucket2_of(mem_p, hash_, sig):
     """gpu_hash.cu:66-67 with the geometry macros of gpu_hash.h:57-69 (only used to AIM probes; the answers come from the kernels)"""
-    hm = (1 << (mem_p - 6)) - 1; bm = (1 << (mem_p - 9)) - 1
-    return ((((hash_ ^ sig) & bm) | (hash_ & ~bm)) & hm).astype(np.uint32)
+    hm = np.uint32((1 << (mem_p - 6)) - 1); bm = np.uint32((1 << (mem_p - 9)) - 1); nbm = np.uint32(~int(bm) & 0xFFFFFFFF)
+    return ((((hash_ ^ sig) & bm) | (hash_ & nbm)) & hm).astype(np.uint32)
 
 
 def case_search_sparse(algo, mem_p, seed, nbuckets=20000):
@@ -237,7 +237,7 @@ def case_serial_sparse(algo, mem_p, seed, nkeys=6000):
     iel["sig"] = (iel["sig"] & np.uint32(~((1 << (mem_p - 9)) - 1) & 0xFFFFFFFF)) | rng.integers(1, 128, nkeys).astype(np.uint32)
     r.insert_one_by_one(iel)
     after_insert = r.dump()
-    dele = iel[::3]
+    dele = np.ascontiguousarray(iel[::3])
     for k in range(len(dele)):
         r.delete(dele[k:k + 1])
     probe = np.concatenate([to_sel(iel), to_sel(reqs(rng, 200))])
