@@ -136,13 +136,14 @@ def test_search_races_insert_on_another_stream(gpu, rng):
     expect = np.concatenate([old["loc"], new["loc"]])
     in_d = mk.DeviceBuffer.from_host(probe)
     new_d = mk.DeviceBuffer.from_host(new)
-    rounds, parts = 12, 24
+    rounds, parts = 12, 25                                           # 25 x 8000 = every new key; the last part after the last search
     outs = [mk.DeviceBuffer(8 * len(probe)) for _ in range(rounds)]
     step = len(new) // parts
     for r in range(rounds):                                          # searches keep coming while the inserts trickle in
         N.check(L.gpuhash_search_ex(C.byref(t.geom), in_d.ptr, outs[r].ptr, t.ptr, len(probe), None, s1))
         for p in (2 * r, 2 * r + 1):
             N.check(L.gpuhash_insert_flat_ex(C.byref(t.geom), t.ptr, new_d.ptr + 12 * step * p, step, None, 0, s2))
+    N.check(L.gpuhash_insert_flat_ex(C.byref(t.geom), t.ptr, new_d.ptr + 12 * step * 24, len(new) - 24 * step, None, 0, s2))
     N.check(L.gpuhash_stream_sync(s1)); N.check(L.gpuhash_stream_sync(s2))
     seen_partial = False
     for r in range(rounds):
@@ -157,32 +158,44 @@ def test_search_races_insert_on_another_stream(gpu, rng):
 
 
 def test_concurrent_high_load_within_the_envelope_of_sequential_orders(gpu, rng):
-    """90 % load, cuckoo, pair layout: the counters of the concurrent launches against sequential oracle runs of the SAME
-    eight launches with the requests of each launch in six random orders.  Which requests overflow their first bucket is
-    nearly order-free; how often chains displace and drop depends on the order, so the concurrent run has to land within the
-    sequential orders' envelope widened by its own width (and by 2 % of the mean)."""
+    """90 % load, cuckoo, pair layout: the counters of concurrent launches against sequential oracle runs of the same requests
+    in six random orders (measured first: tools/dbg_env.py, profiles/r02_concurrent_envelope.md).
+      * 512 launches of ~1 800 requests: the run is nearly sequential and has to land INSIDE the envelope of the sequential
+        orders, widened by the envelope's own width + 1.5 % of the mean (+ 20);
+      * 8 launches of ~118 000 requests: every request of a launch tries its first bucket before the evictions of that
+        launch have re-homed any victim into it, so fewer requests find bucket 1 full (to_b2 6-8 % lower), more of them
+        meet in the alternates (displaced 5-7 % higher) and more chains reach MAX_CUCKOO_NUM (dropped 1.3-1.7 x): a
+        systematic, one-directional shift, asserted as such (round 1 allowed 0.5 x .. 3 x either way)."""
     mem_p = 20
     slots = (1 << mem_p) // 8
     iel = H.random_requests(rng, int(0.9 * slots))
-    parts = np.array_split(iel, 8)
     env = {"to_b2": [], "displaced": [], "dropped": []}
     for k in range(6):
         o = po.Oracle(mem_p, po.CUCKOO)
-        for part in parts:
-            o.insert(part[rng.permutation(len(part))])
+        o.insert(iel[rng.permutation(len(iel))])
         w = o.stats.as_dict()
         for key in env:
             env[key].append(w[key])
-    t = mk.DeviceTable(mem_p, po.CUCKOO, mk.LAYOUT_PAIRS)
-    st = mk.DeviceStats()
-    for part in parts:
-        gpu_insert(t, part, stats=st)
-    s = st.read()
-    got = {"to_b2": s["ins_to_b2"], "displaced": s["ins_displaced"], "dropped": s["ins_dropped"]}
+
+    def concurrent(nparts):
+        t = mk.DeviceTable(mem_p, po.CUCKOO, mk.LAYOUT_PAIRS)
+        st = mk.DeviceStats()
+        for part in np.array_split(iel, nparts):
+            gpu_insert(t, part, stats=st)
+        s = st.read()
+        assert s["ins_gave_up"] == 0
+        pairs = H.occupied_pairs(po.Oracle(mem_p).buckets(t.dump_reference()))
+        assert len(pairs) == len(iel) - s["ins_dropped"] and len(np.unique(pairs)) == len(pairs)
+        t.free()
+        return {"to_b2": s["ins_to_b2"], "displaced": s["ins_displaced"], "dropped": s["ins_dropped"]}
+
+    fine = concurrent(512)
     for key, vals in env.items():
         lo, hi, mean = min(vals), max(vals), float(np.mean(vals))
-        slack = (hi - lo) + 0.02 * mean + 20
-        assert lo - slack <= got[key] <= hi + slack, f"{key}: concurrent {got[key]} outside the sequential envelope [{lo}, {hi}] +- {slack:.0f}"
-    assert s["ins_gave_up"] == 0
-    pairs = H.occupied_pairs(po.Oracle(mem_p).buckets(t.dump_reference()))
-    assert len(pairs) == len(iel) - s["ins_dropped"] and len(np.unique(pairs)) == len(pairs)
+        slack = (hi - lo) + 0.015 * mean + 20
+        assert lo - slack <= fine[key] <= hi + slack, f"{key}: {fine[key]} outside the sequential envelope [{lo}, {hi}] +- {slack:.0f}"
+    coarse = concurrent(8)
+    m = {k: float(np.mean(v)) for k, v in env.items()}
+    assert 0.88 * m["to_b2"] <= coarse["to_b2"] <= 1.0 * m["to_b2"], (coarse, m)
+    assert 1.0 * m["displaced"] <= coarse["displaced"] <= 1.15 * m["displaced"], (coarse, m)
+    assert 1.0 * m["dropped"] <= coarse["dropped"] <= 2.2 * m["dropped"] + 30, (coarse, m)
