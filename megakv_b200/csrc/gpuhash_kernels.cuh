@@ -105,6 +105,13 @@ __device__ __forceinline__ uint32_t ld_u32_ro(const uint32_t* p)
 	return v;
 }
 
+__device__ __forceinline__ uint32_t ld_u32_strong(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global" GH_LTC ".u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ void st_u32_strong(uint32_t* p, uint32_t v)
 {
 	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -417,8 +424,8 @@ __device__ __forceinline__ void insert_one(Bucket* table, const Geom& g,
 				if (expect != want && atomicCAS((unsigned long long*)&bk->w[2 * l], expect, want) != expect) {
 					GH_COUNT(ins_cas_retry); continue;
 				}
-			} else {
-				st_u32_strong(&bk->w[8 + l], loc);
+			} else if (ld_u32_strong(&bk->w[8 + l]) != loc) {         // (a hot key updated with the location it already has -- zipf SETs --
+				st_u32_strong(&bk->w[8 + l], loc);                    //  would otherwise serialise thousands of stores on one word)
 			}
 			GH_COUNT(ins_updated);
 			goto done;
