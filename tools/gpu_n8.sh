@@ -1,6 +1,14 @@
 #!/bin/bash
+# 8 GPUs: both N > 1 modes of the bench (quick: value + parity only), then the real-NVLink tests at world 4 and 8
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/topo8.txt 2>&1
 N=${1:-8}
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 1024 --warmup 64 --verbose > gpurun_out/bench_r2_n$N.json 2> gpurun_out/bench_r2_n$N.err
-echo "rc=$?"; cut -c1-2500 gpurun_out/bench_r2_n$N.json; grep -E "bench r0|Error|error" gpurun_out/bench_r2_n$N.err | tail -12
+run() { # name, env...
+  name=$1; shift
+  env "$@" GPUHASH_BENCH_QUICK=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 2> gpurun_out/r02_n${N}_$name.err | tail -1 | tee gpurun_out/r02_n${N}_$name.json | cut -c1-500
+  grep -v "^\*\|OMP_NUM\|^$\|W1017\|NCCL version" gpurun_out/r02_n${N}_$name.err | tail -3
+}
+run lanes GPUHASH_SHARD_MODE=lanes
+run xchg16x8 GPUHASH_SHARD_MODE=xchg GPUHASH_XCHG_SHAPE=16x8
+run xchg16x4 GPUHASH_SHARD_MODE=xchg GPUHASH_XCHG_SHAPE=16x4
+echo "== tests on $N GPUs"
+timeout 900 python -m pytest tests/test_gpu_xchg.py tests/test_gpu_sharded.py -q -m gpu -k "one_process or sharded_index_on_gpus" 2>&1 | tail -4 | tee gpurun_out/r02_n${N}_pytest.txt
