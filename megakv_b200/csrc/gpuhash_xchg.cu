@@ -92,7 +92,6 @@ struct XArgs {
 	int do_serve;                          /* exchange seq-1 exists */
 	uint2 *g_out; uint32_t g_n;            /* exchange seq-2: where its results go */
 	unsigned long long timeout_ns;
-	int ablate;                            /* experiments only (GPUHASH_XCHG_ABLATE): 1 no inbox stores, 2 no map stores, 4 no gather loads, 8 no gather stores */
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
@@ -237,7 +236,7 @@ __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw
 		*(char **)(runs + 16 + 2 * lane) = dst;
 	}
 	__syncwarp();
-	if (kind == 0 && !(a.ablate & 2)) {                    /* the gather's map: one coalesced 128 B store per round */
+	if (kind == 0) {                    /* the gather's map: one coalesced 128 B store per round */
 		uint32_t *where = (uint32_t *)(a.peer[a.rank] + a.L.where) + (size_t)slot * a.L.cap_s + t0;
 #pragma unroll
 		for (int r = 0; r < 8; r++) {
@@ -246,8 +245,7 @@ __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw
 		}
 	}
 	/* runs out: neighbouring lanes share a run -> contiguous stores, local or over NVLink */
-	if ((a.ablate & 1) && a.seq > 520u) {                  /* (after the experiment's preload and warm-up have filled the inboxes) */
-	} else if (kWords == 2) {
+	if (kWords == 2) {
 #pragma unroll
 		for (int it = 0; it < 8; it++) {
 			const uint32_t q = 32 * it + lane;
@@ -303,7 +301,6 @@ __device__ __forceinline__ void gather_tile(const XArgs &a, uint32_t tile, uint3
 	for (int it = 0; it < 4; it++) {
 		const uint32_t k = 64 * it + 2 * lane;
 		v[2 * it] = make_uint2(0u, 0u); v[2 * it + 1] = make_uint2(0u, 0u);
-		if (a.ablate & 4) continue;
 		if (k < tile_n) {
 			const uint2 *src = mine + (size_t)(pre.w[it].x >> 28) * a.L.cap_s + (pre.w[it].x & 0x0fffffffu);
 			asm volatile("ld.global.ca.v2.u32 {%0,%1}, [%2];" : "=r"(v[2 * it].x), "=r"(v[2 * it].y) : "l"(src));
@@ -318,7 +315,6 @@ __device__ __forceinline__ void gather_tile(const XArgs &a, uint32_t tile, uint3
 #pragma unroll
 	for (int it = 0; it < 4; it++) {
 		const uint32_t k = 64 * it + 2 * lane;
-		if (a.ablate & 8) continue;
 		if (k + 1 < tile_n) {
 			if (vec) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out + k), "r"(v[2 * it].x), "r"(v[2 * it].y), "r"(v[2 * it + 1].x), "r"(v[2 * it + 1].y) : "memory");
 			else { gh::st_stream_u2(out + k, v[2 * it]); gh::st_stream_u2(out + k + 1, v[2 * it + 1]); }
@@ -607,7 +603,7 @@ struct gpuhash_xchg_s {
 	XLayout L; char *arena; char *peer[kMaxShards]; int have_peers;
 	uint32_t seq;
 	struct { void *out; uint32_t n; } pend[3];          /* exchange e: pend[e % 3] */
-	int grid, shape, ablate;
+	int grid, shape;
 	unsigned long long timeout_ns;
 };
 
@@ -642,7 +638,6 @@ extern "C" gpuhash_xchg_t *gpuhash_xchg_create(const gpuhash_geom_t *g, void *ta
 			|| cudaFuncSetAttribute(xchg_step_kernel<false, 24, 8, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8) != cudaSuccess) {
 		cudaFree(x->arena); free(x); return NULL;
 	}
-	e = getenv("GPUHASH_XCHG_ABLATE"); x->ablate = e ? atoi(e) : 0;
 	x->timeout_ns = 2000000000ULL;
 	if (G == 1) { x->peer[0] = x->arena; x->have_peers = 1; }
 	return x;
@@ -693,7 +688,7 @@ extern "C" int gpuhash_xchg_step(gpuhash_xchg_t *x, const void *search_in, size_
 	a.i_in = (const uint32_t *)insert_in; a.i_n = (uint32_t)n_insert;
 	a.do_serve = seq >= 2;
 	if (seq >= 3) { a.g_out = (uint2 *)x->pend[(seq - 2) % 3].out; a.g_n = x->pend[(seq - 2) % 3].n; }
-	a.timeout_ns = x->timeout_ns; a.ablate = x->ablate;
+	a.timeout_ns = x->timeout_ns;
 	x->pend[seq % 3].out = search_out; x->pend[seq % 3].n = (uint32_t)n_search;
 	x->seq = seq;
 	const bool pairs = x->g.layout == GPUHASH_LAYOUT_PAIRS;
