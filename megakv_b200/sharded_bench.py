@@ -53,10 +53,10 @@ def main(args, rank, world, local_rank, log):
     # of the reference's triple-buffered batches, mega_batch.h:74-82).  One exchange routes the W batches of a scheduler
     # cycle at once -- what the reference's cycle does with the batches of all its workers (mega_scheduler.c:393-504).
     GROUP = W
-    # mode "xchg" (the product): ONE kernel per step and GPU (gpuhash_xchg.cu) -- launch j scatters exchange j, serves j-1,
-    # gathers j-2, tiles interleaved by ticket.  mode "lanes": the scatter / serve / gather kernels of gpuhash_shard.cu,
-    # S exchanges in flight on S streams (kept for A/B runs: GPUHASH_SHARD_MODE=lanes).
-    mode = os.environ.get('GPUHASH_SHARD_MODE', 'xchg')
+    # mode "lanes" (default: the faster one, profiles/r02_xchg_ncu.md): the scatter / serve / gather kernels of gpuhash_shard.cu,
+    # S exchanges in flight on S streams.  mode "xchg" (GPUHASH_SHARD_MODE=xchg): ONE warp-specialised kernel per step and GPU
+    # (gpuhash_xchg.cu) -- launch j scatters exchange j, serves j-1, gathers j-2.
+    mode = os.environ.get('GPUHASH_SHARD_MODE', 'lanes')
     S = max(1, min(int(os.environ.get('GPUHASH_LANES', 8)), 16, steps)) if mode == 'lanes' else 1
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)] if mode == 'lanes' else []
