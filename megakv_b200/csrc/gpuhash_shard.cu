@@ -859,6 +859,61 @@ serve_search_staged_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int
 	}
 }
 
+/* serve, op 0, every warp on its own (gh::warp_tile_search, the search kernel's shape): a warp reads a 64-request tile of an
+ * inbox region as ONE 512 B access (the next tile already in flight), probes it with four table loads per lane in flight and
+ * writes the 64 results as ONE 512 B access straight into the origin's staging area (over NVLink when the origin is a peer).
+ * No shared-memory staging, no barrier, no bulk copy; 64 registers, so three CTAs of eight warps per SM leave room for the
+ * scatter / gather kernels of the other lanes to run next to it (the staged kernel: one load per lane in flight, 15.4 Gops/s
+ * alone on 2 GPUs; this shape is the one the 1-GPU search path measures at 20-21).  Tiles are dealt round-robin to the warps of
+ * the (persistent) grid; the last CTA raises the result flags. */
+template <bool kPairs>
+__global__ void __launch_bounds__(256, 3)
+serve_search_warp_kernel(const gh::Bucket *__restrict__ table, gh::Geom g, int G, Ptrs seg_in, const uint32_t *seg_count, Ptrs seg_out, PubArgs pub)
+{
+	__shared__ uint32_t tprefix[kMaxShards + 1], count[kMaxShards];
+	__shared__ const uint2 *in_p[kMaxShards];
+	__shared__ uint2 *out_p[kMaxShards];
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int s = 0; s < kMaxShards; s++) {
+			const uint32_t c = s < G ? ((const volatile uint32_t *)seg_count)[s] : 0u;
+			tprefix[s] = acc; count[s] = c; acc += (c + gh::kTileReq - 1) / gh::kTileReq;
+		}
+		tprefix[kMaxShards] = acc;
+	}
+	if (threadIdx.x < kMaxShards) {
+		in_p[threadIdx.x] = (const uint2 *)seg_in.p[threadIdx.x];
+		out_p[threadIdx.x] = (uint2 *)seg_out.p[threadIdx.x];
+	}
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31u;
+	const uint32_t tiles = tprefix[kMaxShards];
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t h1 = 0, h2 = 0;
+	auto locate = [&](uint32_t t, int &s, uint32_t &j0, uint32_t &valid) {           /* s only moves forward */
+		while (s < kMaxShards - 1 && t >= tprefix[s + 1]) s++;
+		j0 = (t - tprefix[s]) * gh::kTileReq;
+		valid = min((uint32_t)gh::kTileReq, count[s] - j0);
+	};
+	int s = 0, sn = 0; uint32_t j0 = 0, valid = 0, jn = 0, validn = 0;
+	uint32_t t = warp;
+	uint4 v = make_uint4(0u, 0u, 0u, 0u);
+	if (t < tiles) { locate(t, s, j0, valid); v = gh::warp_tile_load<false>(in_p[s] + j0, valid, lane); }
+	sn = s;
+	for (; t < tiles; t += warps) {
+		const uint32_t tn = t + warps;
+		uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+		if (tn < tiles) { locate(tn, sn, jn, validn); vn = gh::warp_tile_load<false>(in_p[sn] + jn, validn, lane); }
+		gh::warp_tile_search<kPairs, false, false>(table, g, in_p[s] + j0, out_p[s] + j0, valid, true, v, lane, h1, h2);
+		s = sn; j0 = jn; valid = validn; v = vn;
+	}
+	if (last_cta_done(pub.ticket)) {
+		if (threadIdx.x < G)
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"((uint32_t *)pub.peer_flag.p[threadIdx.x] + pub.my_rank), "r"(pub.seq) : "memory");
+		if (threadIdx.x == 0) *pub.ticket = 0;
+	}
+}
+
 static int fill_pub(PubArgs &P, int G, int my_rank, const void *const *peer_count_ptrs, const void *const *peer_flag_ptrs,
 		uint32_t *ticket_d, uint32_t seq)
 {
@@ -962,7 +1017,13 @@ extern "C" int gpuhash_serve(const gpuhash_geom_t *g, void *table_d, int op, int
 	const bool pairs = gg.layout == gh::kLayoutPairs;
 #define GH_SERVE(P_, OP_) serve_kernel<P_, OP_><<<blocks, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P, st)
 	if (op == 0) {
-		if (serve_staged()) {
+		static int warp_mode = -1;                        /* GPUHASH_SERVE_MODE=warp | staged (default, until measured otherwise) */
+		if (warp_mode < 0) { const char *e = getenv("GPUHASH_SERVE_MODE"); warp_mode = e && !strcmp(e, "warp") ? 1 : 0; }
+		if (warp_mode) {
+			const unsigned qb = grid_for(((max_total ? max_total : 1) + 63) / 64 * 32 + (size_t)G * 32, env_int("GPUHASH_SERVE_CTAS_PER_SM", 3));
+			if (pairs) serve_search_warp_kernel<true><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, P);
+			else       serve_search_warp_kernel<false><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, P);
+		} else if (serve_staged()) {
 			/* one tile of 64 requests per CTA and iteration; G partial tiles at most on top of max_total / 64 */
 			const unsigned qb = grid_for(((max_total ? max_total : 1) + 63) / 64 * 256 + (size_t)G * 256, env_int("GPUHASH_SERVE_CTAS_PER_SM", 4));
 			if (pairs) serve_search_staged_kernel<true><<<qb, 256, 0, s>>>(t, gg, G, I, seg_count_d, O, req_flags_d, err_d, P);

@@ -8,7 +8,7 @@ run() { # name, env...
   grep -v "^\*\|OMP_NUM\|^$\|W1017\|NCCL version" gpurun_out/r02_n${N}_$name.err | tail -3
 }
 run lanes GPUHASH_SHARD_MODE=lanes
+run lanes16 GPUHASH_SHARD_MODE=lanes GPUHASH_LANES=16
 run xchg16x8 GPUHASH_SHARD_MODE=xchg GPUHASH_XCHG_SHAPE=16x8
-run xchg16x4 GPUHASH_SHARD_MODE=xchg GPUHASH_XCHG_SHAPE=16x4
 echo "== tests on $N GPUs"
 timeout 900 python -m pytest tests/test_gpu_xchg.py tests/test_gpu_sharded.py -q -m gpu -k "one_process or sharded_index_on_gpus" 2>&1 | tail -4 | tee gpurun_out/r02_n${N}_pytest.txt
