@@ -226,8 +226,11 @@ int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_
 
 /* One scheduler cycle for ALL workers in one call and ONE kernel launch (gpuhash_cycle_multi_ex): batches_h[w] holds
  * worker w's HOST buffers and counts, as gpuhash_index_submit takes them one worker at a time.  Zero-copy mode: the
- * buffers are pinned and the kernel reads/writes them itself; else they are staged through the index's per-worker device
- * buffers (n_* within the capacities given to gpuhash_index_create).  Asynchronous: returns a ticket >= 0 (or a negative
+ * buffers are pinned and the kernel reads/writes them itself; else they are staged through device copies owned by the
+ * cycle's slot (n_* within the capacities given to gpuhash_index_create), so that staged cycles in flight overlap (copy-in
+ * of one, kernel of the next, copy-out of a third), and host arrays that are ADJACENT in memory -- worker w+1's array
+ * starting where worker w's ends, as when all batch buffers are carved out of one pinned block -- are moved by ONE copy
+ * per array and direction (multi-megabyte copies run at 48-55 GB/s per direction, 0.5 MB ones at 24).  Asynchronous: returns a ticket >= 0 (or a negative
  * error); gpuhash_index_wait(ticket) returns once that cycle's results are in the host buffers -- up to
  * GPUHASH_INDEX_SLOTS cycles may be in flight, the way the reference's triple-buffered batches allow
  * (src/include/mega_batch.h:74-82); gpuhash_index_sync waits for everything.  Both return 0, a CUDA error, or -3 when a
