@@ -10,8 +10,10 @@ launch (gpuhash_cycle_multi_ex).
   value     whole-job Mops/s with the batches already resident in HBM: CUDA events around exactly K launches; the region is
             measured --reps times and the median reported (all regions listed under "timing")
   e2e       the same K steps through the call a scheduler makes -- gpuhash_index_submit_all / gpuhash_index_wait on PINNED
-            HOST batches (zero-copy: the kernel reads requests and writes results over the host link itself), two cycles in
-            flight -- timed by the HOST'S WALL CLOCK from the first submit to the return of the last wait
+            HOST batches, cycles kept in order (the kernel of cycle k+1 starts when cycle k's has finished, as in the reference),
+            staged through per-slot device copies (the workers' arrays are adjacent in pinned memory, so each array kind is ONE
+            copy per direction), four cycles in flight -- timed by the HOST'S WALL CLOCK from the first submit to the return of
+            the last wait.  ONE fixed path; the zero-copy paths and the unordered mode are listed next to it
   roofline  the same launches with searches only: algorithmic bytes (8 B request + 2 x 32 B signature sectors
             + 32 B location sector per hit bucket + 8 B result = 112 B) / time, against MEASURED_PEAKS.json hbm_gbs; plus
             one bulk launch and the measured random-probe ceiling of the same table
@@ -316,8 +318,9 @@ def main():
     fresh_inserts(insert_d.ptr, N_INSERT * kd)
     N.check(L.gpuhash_device_sync())
 
-    def resident(first_step, count, n_insert=N_INSERT):
+    def resident(first_step, count, n_insert=N_INSERT, streams=None):
         """`count` steps starting at resident step `first_step` (wrapping); one launch per step; returns seconds (CUDA events)"""
+        streams = args.streams if streams is None else streams
         total_ms, done = 0.0, 0
         while done < count:
             s0 = (first_step + done) % ks
@@ -325,7 +328,7 @@ def main():
             res = N.BenchResult()
             b0 = s0 * W
             N.check(L.gpuhash_bench_cycles(C.byref(geom), table, search_d.ptr + 8 * N_SEARCH * b0, N_SEARCH, out_d.ptr + 8 * N_SEARCH * b0,
-                                           insert_d.ptr + 12 * N_INSERT * b0, n_insert, W, c, args.streams, C.byref(res)),
+                                           insert_d.ptr + 12 * N_INSERT * b0, n_insert, W, c, streams, C.byref(res)),
                     "gpuhash_bench_cycles")
             total_ms += res.total_ms; done += c
         return total_ms / 1e3
@@ -340,6 +343,18 @@ def main():
     t_val = float(np.median(regions))
     value = steps * W * BATCH / t_val / 1e6
     log(f"resident: {steps} steps x {W} batches, regions {[round(x * 1e3, 3) for x in regions]} ms -> {value:.1f} Mops/s")
+    # the same steps strictly one after the other (cycle k+1 starts when cycle k has finished, the reference's order)
+    strict = None
+    if args.streams != 1:
+        with sampler:
+            s_reg = []
+            for r in range(3):
+                s_reg.append(resident(warm, steps, streams=1))
+                fresh_inserts(insert_d.ptr, N_INSERT * kd); N.check(L.gpuhash_device_sync())
+        t_st = float(np.median(s_reg))
+        strict = {"Mops/s": round(steps * W * BATCH / t_st / 1e6, 1), "ms_per_step": round(t_st / steps * 1e3, 6),
+                  "regions_ms": [round(x * 1e3, 3) for x in s_reg],
+                  "what": "the same launches on ONE stream: the kernel of step k+1 starts when step k's has finished"}
 
     # ---- parity on the timed output, word for word: every search of the LAST timed step must return the location its key was
     #      inserted with (generator's expect_loc = key index + 1) in exactly one of its two words and 0 in the other
@@ -519,8 +534,7 @@ def main():
         L.gpuhash_event_destroy(ev_a); L.gpuhash_event_destroy(ev_b)
 
     # ---- e2e: the call a scheduler makes -- gpuhash_index_submit_all(W pinned host batches) ... gpuhash_index_wait -- ONE fixed
-    #      path: zero-copy (the cycle kernel reads the requests from and writes the results to the pinned buffers itself) + one
-    #      launch per step, two cycles in flight, HOST WALL CLOCK from the first submit to the return of the last wait.
+    #      path (HEADLINE below), HOST WALL CLOCK from the first submit to the return of the last wait; other paths next to it.
     ke = min(steps + warm, 24)                                       # distinct steps in pinned memory (66 MB each)
     hb = ke * W
     hs = L.gpuhash_host_alloc(8 * N_SEARCH * hb); ho = L.gpuhash_host_alloc(8 * N_SEARCH * hb); hi = L.gpuhash_host_alloc(12 * N_INSERT * hb)
@@ -553,35 +567,34 @@ def main():
         return check_words(ho_np[:2 * n], exp_h[:n], hs_np[:2 * n])[0]
 
     variants = {}
-    L.gpuhash_index_set_zero_copy(ix, 1)
-    e2e_pass(warm)
-    ho_np[:] = 0
+    HEADLINE = "staged copies (adjacent host batches: one copy per array) + one launch per step, cycles ordered, 4 in flight"
+    paths = [   # name, zero_copy, unordered cycles, cycles in flight
+        (HEADLINE, 0, 0, 4),
+        ("staged copies + one launch per step, cycles ordered, 2 in flight", 0, 0, 2),
+        ("zero-copy (the kernel reads / writes the pinned buffers) + one launch per step, cycles ordered, 2 in flight", 1, 0, 2),
+        ("zero-copy + one launch per step, one cycle in flight", 1, 0, 1),
+        ("zero-copy + one launch per step, cycle kernels UNORDERED, 2 in flight", 1, 1, 2),
+    ]
+    t_e = e2e_val = e2e_bad = None
     e_regions = []
-    with sampler:
-        for r in range(3):
-            e_regions.append(e2e_pass(steps))
-    t_e = float(np.median(e_regions))
-    e2e_bad = e2e_check()
-    assert e2e_bad == 0, f"e2e: {e2e_bad} searches came back wrong"
-    e2e_val = steps * W * BATCH / t_e / 1e6
-    variants["zero_copy+one_launch (headline)"] = {"Mops/s": round(e2e_val, 1), "wall_ms": round(t_e * 1e3, 3), "in_flight": 2}
-    log(f"e2e zero-copy, one launch per step: {steps} steps, wall {[round(x * 1e3, 2) for x in e_regions]} ms -> {e2e_val:.1f} Mops/s")
-    # secondary, for context (same wall clock): strictly one cycle at a time; staging copies instead of zero-copy; one result word
-    t1 = e2e_pass(steps, depth=1)
-    variants["zero_copy+one_launch, one cycle in flight"] = {"Mops/s": round(steps * W * BATCH / t1 / 1e6, 1), "wall_ms": round(t1 * 1e3, 3)}
-    L.gpuhash_index_set_zero_copy(ix, 0)
-    for depth in (2, 4):
-        e2e_pass(min(warm, 3), depth=depth); ho_np[:] = 0
-        t2 = float(np.median([e2e_pass(steps, depth=depth) for _ in range(3)]))
-        s_bad = e2e_check()
-        assert s_bad == 0, f"e2e (staged): {s_bad} searches came back wrong"
-        variants[f"staged (adjacent host batches coalesced into one copy per array)+one_launch, {depth} cycles in flight"] = {
-            "Mops/s": round(steps * W * BATCH / t2 / 1e6, 1), "wall_ms": round(t2 * 1e3, 3)}
+    for name, zc, unordered, depth in paths:
+        L.gpuhash_index_set_zero_copy(ix, zc); L.gpuhash_index_set_unordered_cycles(ix, unordered)
+        e2e_pass(max(depth, min(warm, 3)), depth=depth); ho_np[:] = 0      # (every slot in flight is warm: staging buffers are allocated at first use)
+        with sampler:
+            regs = [e2e_pass(steps, depth=depth) for _ in range(3)]
+        t = float(np.median(regs))
+        bad = e2e_check()
+        assert bad == 0, f"e2e ({name}): {bad} searches came back wrong"
+        variants[name] = {"Mops/s": round(steps * W * BATCH / t / 1e6, 1), "wall_ms": round(t * 1e3, 3)}
+        if name == HEADLINE:
+            t_e, e_regions, e2e_bad, e2e_val = t, regs, bad, steps * W * BATCH / t / 1e6
+            log(f"e2e {name}: {steps} steps, wall {[round(x * 1e3, 2) for x in regs]} ms -> {e2e_val:.1f} Mops/s")
+    L.gpuhash_index_set_unordered_cycles(ix, 0)
     # the consumer only ever takes one of the two result words (mega_send.c:411-414): let the device choose and send 4 B
     # per search back instead of 8.  Reported next to the headline, not as it: it changes what search_out holds.
-    L.gpuhash_index_set_zero_copy(ix, 1); L.gpuhash_index_set_compact_results(ix, 1)
-    e2e_pass(min(warm, 3)); ho_np[:] = 0
-    t_c = e2e_pass(steps)
+    L.gpuhash_index_set_zero_copy(ix, 0); L.gpuhash_index_set_compact_results(ix, 1)
+    e2e_pass(min(warm, 3), depth=4); ho_np[:] = 0
+    t_c = e2e_pass(steps, depth=4)
     c_bad = e2e_check(compact=True)
     assert c_bad == 0, f"e2e (compact): {c_bad} searches came back wrong"
     compact_info = {"Mops/s": round(steps * W * BATCH / t_c / 1e6, 1), "wall_ms": round(t_c * 1e3, 3), "d2h_bytes_per_step": 4 * N_SEARCH * W,
@@ -654,11 +667,16 @@ def main():
         "config": workload_config(mem_p, args),
         "timing": {"timed_region_ms": round(t_val * 1e3, 3), "regions_ms": [round(x * 1e3, 3) for x in regions],
                    "what": f"each region = exactly {steps} steps = {steps} launches, CUDA events; median of {len(regions)} regions",
-                   "cycles_in_flight": args.streams},
+                   "cycles_in_flight": args.streams,
+                   "cycle_order": ("strict" if args.streams == 1 else
+                                   f"{args.streams} cycles in flight on {args.streams} streams: the tail of a cycle overlaps the head of the next, so requests of "
+                                   "consecutive cycles are unordered where they overlap -- like workers inside a cycle (mega_scheduler.c:393-502); the "
+                                   "benchmark's requests are independent of each other either way (searches of preloaded keys, inserts of fresh keys)"),
+                   "strict_cycle_order": strict},
         "e2e": {"value": round(e2e_val, 1), "unit": "Mops/s", "h2d_bytes_per_step": (8 * N_SEARCH + 12 * N_INSERT) * W,
                 "d2h_bytes_per_step": 8 * N_SEARCH * W, "wall_ms": round(t_e * 1e3, 3), "regions_wall_ms": [round(x * 1e3, 3) for x in e_regions],
                 "timing": "host wall clock, first gpuhash_index_submit_all to the return of the last gpuhash_index_wait",
-                "path": "zero-copy + one launch per step, 2 cycles in flight", "mismatches": e2e_bad,
+                "path": HEADLINE, "mismatches": e2e_bad,
                 "variants": variants, "ring": ring_info, "compact_results": compact_info},
         "gpu_launches": steps,
         "parity_checked": True, "mismatches": mismatches, "searches_checked": nchk, "orphaned_keys_seen": orphans,

@@ -237,6 +237,12 @@ int gpuhash_index_sync(gpuhash_index_t *ix);                            /* mega_
  * phase wait inside a cycle kernel timed out (the batch is suspect). */
 #define GPUHASH_INDEX_SLOTS 4
 int gpuhash_index_submit_all(gpuhash_index_t *ix, const gpuhash_batch_t *batches_h, int num_batches);
+/* Cycles in flight keep the reference's order by default: the kernel of cycle k+1 starts when the kernel of cycle k has
+ * finished (the reference synchronises the device once per cycle, mega_scheduler.c:504), so a GET submitted one cycle after
+ * a SET sees it; only the copies of neighbouring cycles (staged mode) and the host's submission run ahead.  on != 0 drops
+ * that edge: consecutive cycle kernels may overlap (tail of one, head of the next: ~4 % more throughput on resident
+ * batches) and requests of DIFFERENT cycles in flight are unordered against each other, like workers inside a cycle. */
+int gpuhash_index_set_unordered_cycles(gpuhash_index_t *ix, int on);
 int gpuhash_index_wait(gpuhash_index_t *ix, int ticket);
 
 /* ---- the scheduler cycle without launches (megakv_b200/csrc/gpuhash_ring.cu; north_star (c)) ----

@@ -122,6 +122,7 @@ SYMBOLS = {
     "gpuhash_index_sync": (_i, [_vp]),
     "gpuhash_index_submit_all": (_i, [_vp, C.POINTER(Batch), _i]),
     "gpuhash_index_wait": (_i, [_vp, _i]),
+    "gpuhash_index_set_unordered_cycles": (_i, [_vp, _i]),
     "gpuhash_route_scatter": (_i, [_vp, _sz, _i, C.c_uint32, _i, _vp, _vp, _vp, _sz, _vp]),
     "gpuhash_route_publish": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp]),
     "gpuhash_search_segments": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _sz, _vp, C.c_uint32, _vp, _vp]),

@@ -34,6 +34,8 @@ struct cycle_slot {                 /* one whole-cycle launch in flight (gpuhash
 	/* staged mode: this slot's own device copies of all workers' batches, packed back to back in worker order (allocated at the
 	 * first staged submit): cycles of different slots overlap -- H2D of one, kernel of the next, D2H of a third */
 	char *st_search, *st_out, *st_delete, *st_insert;
+	cudaEvent_t kernel_done;        /* recorded right behind the cycle kernel: the next cycle's kernel waits for it (ordered mode) */
+	int launched;
 	int busy;
 };
 
@@ -54,6 +56,8 @@ struct gpuhash_index_s {
 	int stats_on;
 	int zero_copy;       /* kernels read requests from / write results to the caller's pinned host buffers directly */
 	int compact;         /* search_out_h gets ONE word per request (the sender's choice, mega_send.c:411-414) instead of two */
+	int unordered;       /* 0 (default): the kernel of cycle k+1 starts after the kernel of cycle k has finished, as the reference's
+	                        cycles do (one cudaDeviceSynchronize each, mega_scheduler.c:504): a GET in cycle k+1 sees a SET of cycle k */
 };
 
 extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
@@ -69,6 +73,7 @@ extern "C" void gpuhash_index_destroy(gpuhash_index_t *ix)
 		struct cycle_slot *c = &ix->slot[k];
 		if (c->stream) cudaStreamDestroy(c->stream);
 		if (c->done) cudaEventDestroy(c->done);
+		if (c->kernel_done) cudaEventDestroy(c->kernel_done);
 		if (c->desc_h) cudaFreeHost(c->desc_h);
 		cudaFree(c->desc_d); cudaFree(c->ws_d);
 		cudaFree(c->st_search); cudaFree(c->st_out); cudaFree(c->st_delete); cudaFree(c->st_insert);
@@ -117,6 +122,7 @@ extern "C" gpuhash_index_t *gpuhash_index_create_layout(int mem_p, unsigned algo
 		struct cycle_slot *c = &ix->slot[k];
 		ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
 		  && cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) == cudaSuccess
+		  && cudaEventCreateWithFlags(&c->kernel_done, cudaEventDisableTiming) == cudaSuccess
 		  && cudaHostAlloc((void **)&c->desc_h, sizeof(gpuhash_batch_t) * MAX_WORKERS, cudaHostAllocDefault) == cudaSuccess
 		  && cudaMalloc((void **)&c->desc_d, sizeof(gpuhash_batch_t) * MAX_WORKERS) == cudaSuccess
 		  && cudaMalloc(&c->ws_d, wsn) == cudaSuccess
@@ -348,14 +354,22 @@ extern "C" int gpuhash_index_submit_all(gpuhash_index_t *ix, const gpuhash_batch
 			if ((e = copy_runs(1, dv[kind], hv[kind], nb[kind], num_batches, s)) != cudaSuccess) return -(int)e - 16;
 	}
 	if ((e = cudaMemcpyAsync(c->desc_d, c->desc_h, sizeof(gpuhash_batch_t) * (size_t)num_batches, cudaMemcpyHostToDevice, s)) != cudaSuccess) return -(int)e - 16;
+	if (!ix->unordered) {                                /* cycles keep their order: this kernel behind the previous cycle's kernel */
+		const struct cycle_slot *prev = &ix->slot[(k + GPUHASH_INDEX_SLOTS - 1) % GPUHASH_INDEX_SLOTS];
+		if (prev->launched && (e = cudaStreamWaitEvent(s, prev->kernel_done, 0)) != cudaSuccess) return -(int)e - 16;
+	}
 	int rc = gpuhash_cycle_multi_ex(&ix->geom, ix->table, c->desc_h, c->desc_d, num_batches, ix->compact, c->ws_d, st, s);
 	if (rc) return rc < 0 ? rc : -rc - 16;
+	if ((e = cudaEventRecord(c->kernel_done, s)) != cudaSuccess) return -(int)e - 16;
+	c->launched = 1;
 	if (!ix->zero_copy && (e = copy_runs(0, dv[3], hv[3], nb[3], num_batches, s)) != cudaSuccess) return -(int)e - 16;
 	if ((e = cudaEventRecord(c->done, s)) != cudaSuccess) return -(int)e - 16;
 	c->busy = 1;
 	ix->next_slot++;
 	return (int)k;
 }
+
+extern "C" int gpuhash_index_set_unordered_cycles(gpuhash_index_t *ix, int on) { if (!ix) return -1; ix->unordered = on != 0; return 0; }
 
 extern "C" int gpuhash_index_wait(gpuhash_index_t *ix, int ticket)
 {

@@ -268,3 +268,60 @@ def test_cycle_legacy_segments_two_lanes(gpu, layout, rng):
         assert o.digest(table=t.dump_reference()) == o.digest()
         base = np.concatenate([base[~np.isin(base["loc"], dele["loc"])]] + blocks)      # (the emptied segment's keys never went in)
     assert st.read()["del_zeroed"] == zeroed == 9000
+
+
+def test_submit_all_staged_coalesces_adjacent_host_batches(gpu, layout, rng):
+    """Staged mode with all workers' arrays carved out of ONE host block (worker w+1's array starts where worker w's ends):
+    gpuhash_index_submit_all moves each array kind with one copy per run of adjacent batches.  Runs are broken on purpose
+    (a gap after worker 2, an empty batch, a worker with no searches), four cycles in flight (one per slot), results and
+    table against the oracle."""
+    mem_p, workers = 23, 7
+    ix = mk.GpuHashIndex(mem_p, workers=workers, max_search=1 << 14, max_insert=1 << 12, max_delete=1 << 12, layout=layout)
+    o = po.Oracle(mem_p)
+    live = [H.random_requests(rng, 2500 + 11 * w, loc_base=1 + 100000 * w) for w in range(workers)]
+    for w in range(workers):
+        ix.insert(live[w]); o.insert(live[w])
+    loc0 = 100000 * workers + 1
+    pending = []
+    for cyc in range(6):
+        batches, loc0 = make_cycle(rng, live, loc0, [300, 64, 1, 0, 257, 33][cyc], [200, 0, 17, 129, 64, 5][cyc])
+        if cyc == 3:
+            batches[4]["search"] = batches[4]["search"][:0]
+        want = [o.search(b["search"]) for b in batches]
+        for b in batches:
+            o.delete(b["delete"]); o.insert(b["insert"])
+        # one block per array kind; worker 3 starts 24 bytes late so that its run is not adjacent to worker 2's
+        def carve(key, dt, item):
+            total = sum(len(b[key]) for b in batches) * item + 24
+            block = np.zeros(total, dtype=np.uint8)
+            views, off = [], 0
+            for w, b in enumerate(batches):
+                if w == 3:
+                    off += 24
+                a = np.ascontiguousarray(b[key], dtype=dt).view(np.uint8).reshape(-1)
+                block[off:off + len(a)] = a
+                views.append((off, len(b[key])))
+                off += len(a)
+            return block, views
+        sblk, sv = carve("search", mk.SEL_DT, 8); dblk, dv_ = carve("delete", mk.IEL_DT, 12); iblk, iv = carve("insert", mk.IEL_DT, 12)
+        oblk = np.full(len(sblk), 0xEE, dtype=np.uint8)
+        descs = (N.Batch * workers)()
+        for w in range(workers):
+            descs[w] = N.Batch(sblk.ctypes.data + sv[w][0] if sv[w][1] else None, oblk.ctypes.data + sv[w][0] if sv[w][1] else None,
+                               dblk.ctypes.data + dv_[w][0] if dv_[w][1] else None, iblk.ctypes.data + iv[w][0] if iv[w][1] else None,
+                               sv[w][1], dv_[w][1], iv[w][1], 0)
+        ticket = ix.L.gpuhash_index_submit_all(ix.h, descs, workers)
+        assert ticket >= 0, ticket
+        pending.append((ticket, oblk, sv, want, (sblk, dblk, iblk, descs)))
+        if len(pending) == 4 or cyc == 5:                            # up to GPUHASH_INDEX_SLOTS cycles in flight
+            for (tk, ob, svv, wnt, _keep) in pending:
+                ix.wait(tk)
+                for w in range(workers):
+                    got = ob[svv[w][0]: svv[w][0] + 8 * svv[w][1]].view(np.uint32)
+                    assert np.array_equal(sorted_pairs(got), sorted_pairs(wnt[w])), f"cycle worker {w}"
+            pending = []
+        for w, b in enumerate(batches):
+            keep = ~np.isin(live[w]["loc"], b["delete"]["loc"])
+            live[w] = np.concatenate([live[w][keep], b["insert"]])
+    assert o.digest(table=ix.dump()) == o.digest()
+    ix.close()

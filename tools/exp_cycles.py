@@ -46,7 +46,7 @@ def cycles(W, streams, n_insert, reps=3):
 
 only = os.environ.get("EXP_ONLY")
 for W in ((64,) if only else (16, 64, 128)):
-    for streams in ((1, 2) if only else (1, 2, 3)):
+    for streams in ((1, 2, 3, 4) if only else (1, 2, 3)):
         for n_ins, name in ((N_INSERT, "mixed"), (0, "search")):
             ms = cycles(W, streams, n_ins)
             ops = steps * W * (N_SEARCH + n_ins)
