@@ -105,6 +105,8 @@ def main(args, rank, world, local_rank, log):
         for i in range(count):
             yield ((first_step + i) % ks) * W
 
+    use_x = [None]                                                      # the ShardExchange run_steps drives (None: lanes / `index`)
+
     def run_steps(index, first, count, with_insert=True):
         """exactly `count` steps = `count` exchanges of W batches"""
         if index is not None:                                           # one lane, one stream (NCCL baseline)
@@ -113,11 +115,11 @@ def main(args, rank, world, local_rank, log):
                 if with_insert:
                     index.insert(ins_f[b * N_INSERT:(b + W) * N_INSERT])
             return
-        if xch is not None:                                             # count + 2 launches: the pipeline fills and drains inside the region
+        if use_x[0] is not None:                                        # count + 2 launches: the pipeline fills and drains inside the region
             for b in cycles_of(first, count):
-                xch.step(sel_f[b * N_SEARCH:(b + W) * N_SEARCH], out_f[b * N_SEARCH:(b + W) * N_SEARCH], None,
-                         ins_f[b * N_INSERT:(b + W) * N_INSERT] if with_insert else None)
-            xch.flush()
+                use_x[0].step(sel_f[b * N_SEARCH:(b + W) * N_SEARCH], out_f[b * N_SEARCH:(b + W) * N_SEARCH], None,
+                              ins_f[b * N_INSERT:(b + W) * N_INSERT] if with_insert else None)
+            use_x[0].flush()
             return
         cur = torch.cuda.current_stream()
         for st in streams:
@@ -193,6 +195,7 @@ def main(args, rank, world, local_rank, log):
                 acc[k] += ev[k].elapsed_time(ev[k + 1]) * 1e3
         return {n: round(a / count, 2) for n, a in zip(names, acc)}
 
+    use_x[0] = xch
     use_graph = not os.environ.get('GPUHASH_NO_GRAPH')
     try:
         timed(None, 0, warm, use_graph)                                 # warm-up
@@ -224,6 +227,38 @@ def main(args, rank, world, local_rank, log):
                     "us_per_step": round(t_val / steps * 1e6, 2), "mismatches": mism, "orphans": orphans})
         dist.barrier(); dist.destroy_process_group()
         return 0
+    # ---- the same steps with STRICT order between consecutive cycles: the fused exchange kernel (gpuhash_xchg.cu; exchange j is
+    #      served entirely by launch j+1, so cycle j+1 sees everything cycle j did).  The lanes above keep S exchanges in flight,
+    #      unordered against each other like workers inside one cycle of the reference.
+    ordered = None
+    if xch is None:
+        try:
+            xo = ShardExchange(plan, rank, GROUP * N_SEARCH, GROUP * N_INSERT, table=be.table)
+            xo.connect(dist)
+            use_x[0] = xo
+            fresh_inserts(); torch.cuda.synchronize()
+            timed(None, 0, warm, use_graph)
+            with sampler:
+                o_reg = []
+                for r in range(3):
+                    fresh_inserts(); torch.cuda.synchronize()
+                    o_reg.append(timed(None, warm, steps, use_graph))
+            assert xo.error() == 0, "a wait inside the exchange kernel timed out"
+            o_mism, o_orph, o_chk = parity_of_step(warm + steps - 1)
+            t_o = float(np.median(o_reg))
+            ordered = {"Mops/s": round(world * steps * W * BATCH / t_o / 1e6, 1), "per_gpu_Mops": round(steps * W * BATCH / t_o / 1e6, 1),
+                       "ms_per_step": round(t_o / steps * 1e3, 6), "regions_ms": [round(x * 1e3, 3) for x in o_reg],
+                       "launches_per_region": steps + 2, "mismatches": o_mism, "searches_checked": o_chk,
+                       "what": "ONE warp-specialised kernel per cycle and GPU (scatter of cycle j, serve of j-1, gather of j-2; peer stores over NVLink, "
+                               "one stream mem-op wait per launch, no wait inside any kernel): cycles strictly ordered"}
+            assert o_mism == 0, f"ordered mode: {o_mism} of {o_chk} routed searches returned something else than their key's location"
+        except AssertionError:
+            raise
+        except Exception as e:                                          # a secondary leg must not take the line down
+            ordered = {"failed": repr(e)}
+        finally:
+            use_x[0] = None
+            fresh_inserts(); torch.cuda.synchronize()
     with sampler:
         t_s = float(np.median([timed(None, warm, steps, use_graph, with_insert=False) for _ in range(min(reps, 3))]))   # search path only (roofline)
     phases = phase_profile(8)
@@ -309,7 +344,8 @@ def main(args, rank, world, local_rank, log):
         assert int((~ok_ & ~unf).sum()) == 0 and unf.mean() < 1e-4, f"e2e ({name}) results came back wrong: {int((~ok_).sum())}"
         e2e_variants[name if g_ok else name.replace("+graph", "")] = round(world * e_steps * W * BATCH / t_e / 1e6, 1)
         log(f"e2e {name}: {e_steps} steps in {t_e * 1e3:.2f} ms (wall)")
-    e2e_path = "zero_copy+graph" if "zero_copy+graph" in e2e_variants else "zero_copy"       # ONE fixed path is the headline
+    # ONE fixed path is the headline: staged copies (as at one GPU); the fused-kernel mode only has the zero-copy path
+    e2e_path = next(k for k in (("staged+graph", "staged") if xch is None else ("zero_copy+graph", "zero_copy")) if k in e2e_variants)
     e2e_val = e2e_variants[e2e_path]
     assert be.p2p_error() + sum(l.be.p2p_error() for l in lanes) + (abs(xch.error()) if xch else 0) == 0, "a flag wait timed out"
 
@@ -327,6 +363,9 @@ def main(args, rank, world, local_rank, log):
                                  "peer stores over NVLink, one stream mem-op wait per launch (gpuhash_xchg.cu)") if xch is not None
                                 else "peer stores + flags, scatter / serve / gather kernels over lanes (gpuhash_shard.cu)",
                     "lanes": S,
+                    "cycle_order": ("strict (exchange j is served entirely by launch j+1)" if xch is not None else
+                                    f"{S} exchanges in flight on {S} streams, unordered against each other like workers inside one cycle of the reference "
+                                    "(mega_scheduler.c:393-502); the benchmark's requests are independent of each other; see ordered_cycles for the strict mode"),
                     "wait_mode": "stream mem-ops" if L.gpuhash_wait_mode() == 1 else "kernel",
                     "parallelism": f"shard{world}"})
         line = {
@@ -347,7 +386,7 @@ def main(args, rank, world, local_rank, log):
                          "peak_source": peak_src, "note": "search path only, includes both NVLink exchanges"},
             "nccl_baseline": {"value": round(world * kb * W * BATCH / t_nccl / 1e6, 1), "unit": "Mops/s", "steps": kb,
                               "what": "same steps, exchanges through torch.distributed all_to_all_single"},
-            "phase_us_one_lane": phases,
+            "phase_us_one_lane": phases, "ordered_cycles": ordered,
             "cpu_baseline": None, "clocks": sampler.summary(), "search_hit_fraction": round(hit, 5),
         }
         B.emit(line)
