@@ -325,3 +325,29 @@ def test_submit_all_staged_coalesces_adjacent_host_batches(gpu, layout, rng):
             live[w] = np.concatenate([live[w][keep], b["insert"]])
     assert o.digest(table=ix.dump()) == o.digest()
     ix.close()
+
+
+def test_unordered_cycles_switch_keeps_independent_cycles_exact(gpu, rng):
+    """gpuhash_index_set_unordered_cycles(1): consecutive cycle kernels may overlap; cycles whose requests do not depend on
+    each other (searches of keys that were there before, inserts of fresh keys -- the benchmark's workload) stay exact."""
+    mem_p, workers = 23, 4
+    ix = mk.GpuHashIndex(mem_p, workers=workers, max_search=1 << 14, max_insert=1 << 12, max_delete=1 << 12)
+    assert ix.L.gpuhash_index_set_unordered_cycles(ix.h, 1) == 0
+    o = po.Oracle(mem_p)
+    old = [H.random_requests(rng, 4000, loc_base=1 + 100000 * w) for w in range(workers)]
+    for w in range(workers):
+        ix.insert(old[w]); o.insert(old[w])
+    tickets, loc0 = [], 10**6
+    for cyc in range(4):                                             # four cycles in flight, nothing waited for in between
+        batches = []
+        for w in range(workers):
+            fresh = H.random_requests(rng, 500, loc_base=loc0); loc0 += 500
+            batches.append({"search": H.to_sel(old[w][cyc::4]), "insert": fresh})
+            o.insert(fresh)
+        tickets.append((ix.submit_all(batches), [o.search(b["search"]) for b in batches]))
+    for (ticket, outs), want in tickets:
+        ix.wait(ticket)
+        for w in range(workers):
+            assert np.array_equal(sorted_pairs(outs[w]), sorted_pairs(want[w]))
+    assert o.digest(table=ix.dump()) == o.digest()
+    ix.close()
