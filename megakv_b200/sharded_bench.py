@@ -57,7 +57,7 @@ def main(args, rank, world, local_rank, log):
     # S exchanges in flight on S streams.  mode "xchg" (GPUHASH_SHARD_MODE=xchg): ONE warp-specialised kernel per step and GPU
     # (gpuhash_xchg.cu) -- launch j scatters exchange j, serves j-1, gathers j-2.
     mode = os.environ.get('GPUHASH_SHARD_MODE', 'lanes')
-    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 16)), 16, steps)) if mode == 'lanes' else 1      # (8 lanes: 2 % slower at 2 and at 8 GPUs)
+    S = max(1, min(int(os.environ.get('GPUHASH_LANES', 20)), 32, steps)) if mode == 'lanes' else 1      # (exchanges in flight; 8 / 16 / 20 at 2 GPUs: 250 / 250 / 243 us per step)
     quick = bool(os.environ.get('GPUHASH_BENCH_QUICK'))
     lanes = [ShardedIndex(CudaShardBackend(plan, rank, GROUP * BATCH, table=be.table), plan, exchange="p2p") for _ in range(S)] if mode == 'lanes' else []
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
