@@ -1,7 +1,6 @@
 #!/bin/bash
-# last check of the tree as committed: CPU-visible build info, full GPU suite, smoke, the two bench arms
 mkdir -p gpurun_out
-echo "== pytest gpu full"; timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_final.txt 2>&1; tail -4 gpurun_out/pytest_gpu_final.txt; grep -E "^E  |^FAILED" gpurun_out/pytest_gpu_final.txt | head
-echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
-echo "== bench"; timeout 900 python bench.py --verbose > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "rc=$? lines=$(wc -l < gpurun_out/bench_r01.json)"; cut -c1-200 gpurun_out/bench_r01.json; grep -E "resident|e2e|ring" gpurun_out/bench_r01.err
-echo "== bench reference arm"; timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$? lines=$(wc -l < gpurun_out/bench_ref.json)"; cut -c1-200 gpurun_out/bench_ref.json
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== full gpu suite"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/r02_pytest_gpu.txt
+echo "== bench N=1 (driver's call shape)"; timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 --verbose > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; grep -v "config" gpurun_out/r02_bench_n1.err | tail -6; cut -c1-300 gpurun_out/r02_bench_n1.json
+echo "== reference arm"; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; cut -c1-400 gpurun_out/r02_bench_ref.json
