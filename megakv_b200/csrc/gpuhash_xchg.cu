@@ -23,7 +23,7 @@
  * registers each (the cycle kernel's shape, gpuhash_kernels.cuh).  Routing is streaming traffic plus shuffling through
  * shared memory: little state, long dependent chains.  Run by the same warps one after the other, every microsecond a
  * warp routes is a microsecond it has no probes in flight (first version of this file: 12.5 Gops/s on one GPU against
- * 20.4 for the lookups alone).  So the CTA (one per SM) is WARP-SPECIALISED: 16 lookup warps + 4 (or 8) router warps,
+ * 20.4 for the lookups alone).  So the CTA (one per SM) is WARP-SPECIALISED: 16 lookup warps + 8 (or 4) router warps,
  * and the register file is re-cut between them at kernel entry with setmaxnreg (the routers give registers up, the
  * lookup warps take them), so that the routers are extra residents, not a tax on the lookups.  Each role has its own
  * ticket counter:
@@ -41,8 +41,9 @@
  * A scatter tile (one warp): 256 requests, owner = top bits of bucket 1 (== of bucket 2 and of every eviction target,
  * gpu_hash.h:67-69), rank inside (tile, owner) by ballots, one global atomic per (tile, owner) reserves the run in the
  * owner's region, the tile is sorted through shared memory and every run leaves as contiguous stores.  The map the gather
- * needs: one byte per request (its place in the sorted tile) + 64 B per tile (run starts, lengths).  A gather tile reads
- * the runs back contiguously and writes the results in request order.
+ * needs: one 32-bit word per request (owner << 28 | index in the owner's region = where its result will be staged).  A gather
+ * tile issues the eight loads of each lane at once (the 256 results of a tile lie in at most G contiguous runs, 2 KB in all)
+ * and writes the results in request order, 512 B per warp store.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -180,7 +181,8 @@ struct RouterSmem {                        /* per router warp */
 };
 
 /* what a router ticket means: even -> scatter tile t/2, odd -> gather tile t/2 (either may not exist) */
-struct RTile { int kind; uint32_t idx; const uint32_t *in; uint32_t n; int words; };   /* kind 0 none, 1 scatter (0..2 = search/delete/insert in `sub`), 3 gather */
+enum { kNone = 0, kScatterSearch, kScatterDelete, kScatterInsert, kGather };
+struct RTile { int kind; uint32_t idx; const uint32_t *in; uint32_t n; int words; };   /* idx: tile inside its request array / result array */
 
 template <int kWords>
 __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw, uint32_t tile, uint32_t tile_n, int kind, uint32_t slot,
@@ -337,19 +339,19 @@ __device__ __forceinline__ void router_loop(const XArgs &a, const Plan &P, Route
 	}
 	__syncwarp();
 	auto decode = [&](uint32_t t) -> RTile {
-		RTile r; r.kind = 0; r.idx = t >> 1; r.in = nullptr; r.n = 0; r.words = 2;
+		RTile r; r.kind = kNone; r.idx = t >> 1; r.in = nullptr; r.n = 0; r.words = 2;
 		if (t >= total) return r;
-		if (t & 1u) { if (r.idx < P.nZ) r.kind = 3; return r; }
+		if (t & 1u) { if (r.idx < P.nZ) r.kind = kGather; return r; }
 		if (r.idx >= nX) return r;
-		if (r.idx < P.xfirst[1])      { r.kind = 1; r.in = (const uint32_t *)a.s_in; r.n = a.s_n; }
-		else if (r.idx < P.xfirst[2]) { r.kind = 2; r.in = a.d_in; r.n = a.d_n; r.idx -= P.xfirst[1]; r.words = 3; }
-		else                          { r.kind = 2 + 8; r.in = a.i_in; r.n = a.i_n; r.idx -= P.xfirst[2]; r.words = 3; }
+		if (r.idx < P.xfirst[1])      { r.kind = kScatterSearch; r.in = (const uint32_t *)a.s_in; r.n = a.s_n; }
+		else if (r.idx < P.xfirst[2]) { r.kind = kScatterDelete; r.in = a.d_in; r.n = a.d_n; r.idx -= P.xfirst[1]; r.words = 3; }
+		else                          { r.kind = kScatterInsert; r.in = a.i_in; r.n = a.i_n; r.idx -= P.xfirst[2]; r.words = 3; }
 		return r;
 	};
 	/* bring a scatter tile's raw requests into stage s: one bulk copy when the piece is 16 B-granular, plain loads else.
 	 * Returns 1 if the mbarrier of the stage will complete for it. */
 	auto fetch = [&](const RTile &tl, int s) -> uint32_t {
-		if (tl.kind == 0 || tl.kind == 3) return 0u;
+		if (tl.kind == kNone || tl.kind == kGather) return 0u;
 		const uint32_t t0 = tl.idx * kRTile, tile_n = min(kRTile, tl.n - t0);
 		const uint32_t bytes = tile_n * tl.words * 4;
 		const uint32_t *src = tl.in + (size_t)tl.words * t0;
@@ -374,7 +376,7 @@ __device__ __forceinline__ void router_loop(const XArgs &a, const Plan &P, Route
 	uint32_t phases = 0;
 	uint32_t bulk = fetch(cur, 0);
 	GPre gp = {};
-	if (cur.kind == 3) gp = gather_prefetch(a, cur.idx, slot_z, lane);
+	if (cur.kind == kGather) gp = gather_prefetch(a, cur.idx, slot_z, lane);
 	while (t < total) {
 		const uint32_t tn = __shfl_sync(0xffffffffu, raw_n, 0);
 		raw_n = lane == 0 ? atomicAdd(ws + kWsTicketR, 1u) : 0u;      /* the ticket after next: its latency is nobody's critical path */
@@ -382,15 +384,16 @@ __device__ __forceinline__ void router_loop(const XArgs &a, const Plan &P, Route
 		__syncwarp();                                      /* stage s^1 was read (sorted out of it) two tiles ago by every lane */
 		const uint32_t bulk_n = fetch(nxt, s ^ 1);
 		GPre gp_n = {};
-		if (nxt.kind == 3) gp_n = gather_prefetch(a, nxt.idx, slot_z, lane);
-		if (cur.kind == 3) {
+		if (nxt.kind == kGather) gp_n = gather_prefetch(a, nxt.idx, slot_z, lane);
+		if (cur.kind == kGather) {
 			gather_tile(a, cur.idx, slot_z, gp, lane);
 		} else if (cur.kind) {
 			if (bulk) { gh::mbar_wait(gh::smem_u32(&S.bar[s]), (phases >> s) & 1u); phases ^= 1u << s; }
 			else __syncwarp();
 			const uint32_t tile_n = min(kRTile, cur.n - cur.idx * kRTile);
-			if (cur.kind == 1) scatter_tile<2>(a, S.raw[s], cur.idx, tile_n, 0, slot_x, S.sorted, S.runs, lane);
-			else               scatter_tile<3>(a, S.raw[s], cur.idx, tile_n, cur.kind == 2 ? 1 : 2, slot_x, S.sorted, S.runs, lane);
+			/* scatter_tile's `kind`: 0 search, 1 delete, 2 insert (index of the inbox and of the counters) */
+			if (cur.kind == kScatterSearch) scatter_tile<2>(a, S.raw[s], cur.idx, tile_n, 0, slot_x, S.sorted, S.runs, lane);
+			else                            scatter_tile<3>(a, S.raw[s], cur.idx, tile_n, cur.kind == kScatterDelete ? 1 : 2, slot_x, S.sorted, S.runs, lane);
 		}
 		t = tn; cur = nxt; bulk = bulk_n; gp = gp_n; s ^= 1;
 	}

@@ -159,7 +159,7 @@ def test_search_races_insert_on_another_stream(gpu, rng):
 
 def test_concurrent_high_load_within_the_envelope_of_sequential_orders(gpu, rng):
     """90 % load, cuckoo, pair layout: the counters of concurrent launches against sequential oracle runs of the same requests
-    in six random orders (measured first: tools/dbg_env.py, profiles/r02_concurrent_envelope.md).
+    in six random orders (measured first: tools/exp_concurrent_envelope.py, profiles/r02_concurrent_envelope.md).
       * 512 launches of ~1 800 requests: the run is nearly sequential and has to land INSIDE the envelope of the sequential
         orders, widened by the envelope's own width + 1.5 % of the mean (+ 20);
       * 8 launches of ~118 000 requests: every request of a launch tries its first bucket before the evictions of that
