@@ -505,8 +505,11 @@ static int launch_cycle_multi(const gpuhash_geom_t *g, void *table_d, gh::MultiA
 	{	/* requests per delete / insert tile (16, 32 or 64) */
 		static int upd_env = -1;
 		if (upd_env < 0) { const char *e = getenv("GPUHASH_UPD_TILE"); upd_env = e && (atoi(e) == 16 || atoi(e) == 32 || atoi(e) == 64) ? atoi(e) : 0; }
-		a.upd_tile = upd_env ? (uint32_t)upd_env : 16u;   /* 64-request update tiles leave the last phase of a 64-batch cycle 1.4 tiles per warp:
-		                                                    a cycle on its own takes 215.8 us with 64, 211.0 with 16 */
+		/* search-heavy cycles (the caller leaves upd_tile 0) take 16-request update tiles: with 64 the last phase of a 95/5 cycle of
+		 * 64 batches is 1.4 tiles per warp (a cycle on its own: 215.8 us with 64, 211.0 with 16); update-heavy cycles (the caller
+		 * presets 64: updates >= a quarter of the requests) keep 64 -- a 50/50 cycle loses a quarter with 16 (tickets, waits) */
+		if (upd_env) a.upd_tile = (uint32_t)upd_env;
+		else if (threads == 64u || a.upd_tile != 64u) a.upd_tile = 16u;
 	}
 	{
 		int dev = 0;
@@ -566,12 +569,17 @@ extern "C" int gpuhash_cycle_multi_ex(const gpuhash_geom_t *g, void *table_d, co
 	static_assert(sizeof(gpuhash_batch_t) == sizeof(gh::BatchDesc), "descriptor mirror");
 	if (!g || g->layout > GPUHASH_LAYOUT_REFERENCE || !table_d || !batches_d || !workspace_d) return -1;
 	if (num_batches < 1 || num_batches > gh::kMaxBatches) return -1;
-	size_t tiles = 0;
+	size_t tiles = 0, n_s = 0, n_u = 0;
 	if (batches_h) {
-		for (int w = 0; w < num_batches; w++) { if (!batch_ok(&batches_h[w], compact)) return -1; tiles += tiles_of_batch(&batches_h[w]); }
+		for (int w = 0; w < num_batches; w++) {
+			if (!batch_ok(&batches_h[w], compact)) return -1;
+			tiles += tiles_of_batch(&batches_h[w]);
+			n_s += batches_h[w].n_search; n_u += (size_t)batches_h[w].n_delete + batches_h[w].n_insert;
+		}
 		if (tiles == 0) return 0;
 	}
 	gh::MultiArgs a; memset(&a, 0, sizeof a);
+	if (!batches_h || 3 * n_u >= n_s) a.upd_tile = 64;       /* update-heavy (or unknown): see launch_cycle_multi */
 	a.descs = (const gh::BatchDesc *)batches_d; a.W = num_batches;
 	a.ws = (uint32_t *)workspace_d;
 	return launch_cycle_multi(g, table_d, a, tiles, compact, stats_d, (cudaStream_t)stream);
@@ -615,6 +623,7 @@ extern "C" int gpuhash_cycle_ws_ex(const gpuhash_geom_t *g, void *table_d,
 		 * (batch_max_insert_job = 4096, mega.c:143) for the grid; the kernel itself reads the real counts */
 		tiles += (size_t)num_blks * (4096 / gh::kTileReq);
 	}
+	if (blk_input_d || 3 * (n_delete + n_insert) >= n_search) a.upd_tile = 64;      /* update-heavy (or sizes only known on the device) */
 	if (workspace_d) a.ws = (uint32_t *)workspace_d;
 	else {
 		int dev = 0;
