@@ -353,7 +353,11 @@ int   gpuhash_ipc_close(void *imported_ptr);
  *   gpuhash_xchg_flush  two steps without new requests: afterwards (and after synchronising the stream) every earlier
  *                       exchange is complete and its results are in place.
  *   gpuhash_xchg_error  0, a CUDA error, or -3 if a wait inside a kernel timed out.
- * Sequence numbers are baked into the launches: a CUDA graph that captured steps may be replayed once. */
+ * Sequence numbers are baked into the launches: a CUDA graph that captured steps may be replayed once.
+ * The kernel is persistent -- one CTA of 640 / 768 threads per SM, the whole register file -- and its delete / insert
+ * tiles wait (bounded: 2 s, then gpuhash_xchg_error reports -3) until every lookup warp of the grid has run out of lookup
+ * tiles, so all its CTAs must be able to become resident: one exchange object per GPU at a time, on a GPU the process has
+ * to itself (no MPS partition smaller than the device).  Between ranks nothing inside a kernel ever waits. */
 typedef struct gpuhash_xchg_s gpuhash_xchg_t;
 gpuhash_xchg_t *gpuhash_xchg_create(const gpuhash_geom_t *g, void *table_d, uint32_t hash_mask_total, int log2_shards,
 		int my_rank, size_t cap_search, size_t cap_update);
