@@ -104,13 +104,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
 	uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
-/* run (owner) of position q in a sorted tile; off[1..7] = run starts, all in shared memory */
-__device__ __forceinline__ int run_of(const uint32_t *off, uint32_t q)
-{
-	return (int)(q >= off[1]) + (int)(q >= off[2]) + (int)(q >= off[3]) + (int)(q >= off[4])
-	     + (int)(q >= off[5]) + (int)(q >= off[6]) + (int)(q >= off[7]);
-}
-
 struct Plan {                              /* built once per CTA in shared memory */
 	uint32_t xfirst[4];                    /* scatter tiles: search | delete | insert */
 	uint32_t ycnt[kMaxShards], yfirst[kMaxShards + 1];      /* lookup tiles per source */
@@ -190,30 +183,30 @@ __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw
 {
 	const uint32_t t0 = tile * kRTile;
 	const int G = a.G;
-	/* rank inside (tile, owner): ballots; the running counts are warp-uniform registers.  Request k = 32 r + lane. */
-	uint32_t run[kMaxShards], key[8];      /* key = owner << 16 | rank */
-#pragma unroll
-	for (int o = 0; o < kMaxShards; o++) run[o] = 0;
-	const uint32_t lt_mask = (1u << lane) - 1u;
+	/* rank inside (tile, owner): one shared-memory atomic per request on the owner's counter (any order inside an owner will do:
+	 * where[] records the place).  Request k = 32 r + lane.  (First version: 8 ballots per round and owner with warp-uniform
+	 * running counts -- 450 of the tile's ~1000 instructions; a router warp is bound by its own instruction latency.) */
+	uint32_t key[8];                       /* owner << 16 | rank */
+	if (lane < kMaxShards) runs[40 + lane] = 0;
+	__syncwarp();
 #pragma unroll
 	for (int r = 0; r < 8; r++) {
 		const uint32_t k = 32 * r + lane;
-		const uint32_t d = k < tile_n ? (raw[kWords * k + 1] & a.hash_mask_total) >> a.shift : 0xffu;      /* owner = top bits of bucket 1 */
-		uint32_t rk = 0;
-#pragma unroll
-		for (int o = 0; o < kMaxShards; o++) {
-			if (o < G) {
-				const uint32_t b = __ballot_sync(0xffffffffu, d == (uint32_t)o);
-				if (d == (uint32_t)o) rk = run[o] + __popc(b & lt_mask);
-				run[o] += __popc(b);
-			}
+		uint32_t d = 0xffu, rk = 0;
+		if (k < tile_n) {
+			d = (raw[kWords * k + 1] & a.hash_mask_total) >> a.shift;              /* owner = top bits of bucket 1 */
+			rk = G == 1 ? k : atomicAdd(&runs[40 + d], 1u);
 		}
 		key[r] = (d << 16) | rk;
 	}
+	__syncwarp();
 	/* lane o: reserve owner o's run in its region; the atomic's round trip hides behind the sorting below */
-	uint32_t mine = 0, off_mine = 0;
+	uint32_t mine = 0;
+	if (lane < kMaxShards) mine = G == 1 ? (lane == 0 ? tile_n : 0u) : runs[40 + lane];
+	uint32_t inc = mine;
 #pragma unroll
-	for (int o = 0; o < kMaxShards; o++) { if ((int)lane == o) mine = run[o]; if ((int)lane > o) off_mine += run[o]; }
+	for (int dd = 1; dd < kMaxShards; dd <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd); if ((int)lane >= dd) inc += o; }
+	const uint32_t off_mine = inc - mine;
 	uint32_t base = 0;
 	uint32_t *counts = (uint32_t *)(a.peer[a.rank] + a.L.counts) + (slot * 3 + kind) * 8;
 	if (lane < (unsigned)G && mine) base = atomicAdd(counts + lane, mine);
@@ -247,12 +240,16 @@ __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw
 		}
 	}
 	/* runs out: neighbouring lanes share a run -> contiguous stores, local or over NVLink */
+	const uint32_t t1 = runs[1], t2 = runs[2], t3 = runs[3], t4 = runs[4], t5 = runs[5], t6 = runs[6], t7 = runs[7];   /* run starts */
+	auto owner_at = [&](uint32_t q) -> int {
+		return (int)(q >= t1) + (int)(q >= t2) + (int)(q >= t3) + (int)(q >= t4) + (int)(q >= t5) + (int)(q >= t6) + (int)(q >= t7);
+	};
 	if (kWords == 2) {
 #pragma unroll
 		for (int it = 0; it < 8; it++) {
 			const uint32_t q = 32 * it + lane;
 			if (q < tile_n) {
-				const int o = run_of(runs, q);
+				const int o = owner_at(q);
 				uint2 *dst = *(uint2 **)(runs + 16 + 2 * o) + q;
 				*dst = *(const uint2 *)(sorted + 2 * q);
 			}
@@ -263,7 +260,7 @@ __device__ __forceinline__ void scatter_tile(const XArgs &a, const uint32_t *raw
 			const uint32_t wq = 32 * it + lane;
 			if (wq < 3 * tile_n) {
 				const uint32_t q = wq / 3;
-				const int o = run_of(runs, q);
+				const int o = owner_at(q);
 				uint32_t *dst = *(uint32_t **)(runs + 16 + 2 * o) + wq;
 				*dst = sorted[wq];
 			}
